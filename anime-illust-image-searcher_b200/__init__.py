@@ -1,0 +1,10 @@
+"""B200-native query-time search scoring for anime-illust-image-searcher (webui.py hot path).
+
+Import as ``ais_b200`` (see ../ais_b200.py).  Sub-modules:
+  synth      synthetic index / query generator (numpy)
+  binding    ctypes view of the C-ABI in include/ais_b200.h (libais_b200.so, sm_100a)
+  engine     SearchEngine: stages an index into HBM and runs the CUDA path
+  webui_api  the callables webui.py uses (load_model, find_similar_documents, ...)
+  shard      doc-sharded multi-GPU search over torch.distributed
+"""
+__all__ = ["synth"]
