@@ -1,0 +1,1135 @@
+// ais_b200 engine: the C ABI of include/ais_b200.h over the sm_100a kernels in scan.cuh,
+// bm25.cuh and select.cuh.  One engine == one GPU == one contiguous shard of the documents.
+//
+// Per query batch (<= max_batch queries share every pass over the doc vectors):
+//   stage_score    bm25_kernel (fp64, bit-exact)  +  scan_kernel (fp32 dot, one pass over the rows)
+//                  -> this shard's {max bm25, max dot}                      webui.py:352,374
+//   stage_combine  final = 0.5*bm25/max + 0.5*dot/max, block top-k, merge    webui.py:376-383,191-195
+//   stage_top      global top-`depth` docs (PRF seeds), optional row gather  webui.py:193-199
+//   stage_requery  re-query vector (host callback or device centroid), 2nd scan,
+//                  R = 0.7*final + 0.3*rer, max(R), block top-k without the seeds  webui.py:200-217
+//   stage_finish   merge, normalise, filter_searched_result, [:topn]         webui.py:219-246,63-80
+// ais_search chains the stages on one GPU; a doc-sharded caller puts its collectives between them.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/ais_b200.h"
+#include "bm25.cuh"
+#include "common.cuh"
+#include "scan.cuh"
+#include "select.cuh"
+
+using namespace ais;
+
+namespace {
+
+thread_local char g_err[768] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(AIS_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+#define TRY(call)                  \
+    do {                           \
+        int _s = (call);           \
+        if (_s != AIS_OK) return _s; \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int MERGE_GROUP = 16;
+constexpr int SEL_MIN_CHUNK = 4096;
+
+// ---- tiny helper kernels ----------------------------------------------------------------------
+__global__ void init_keys_kernel(uint32_t* maxs, uint64_t* maxb, uint64_t* maxr, int32_t* status, int nq, int which) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    if (which & 1) { maxs[i] = fkey(-INFINITY); maxb[i] = dkey(-INFINITY); status[i] = 0; }
+    if (which & 2) { maxs[i] = fkey(-INFINITY); maxr[i] = dkey(-INFINITY); }
+}
+__global__ void maxes_kernel(const uint64_t* maxb, const uint32_t* maxs, int nq, double* maxes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    maxes[2 * i] = dkey_inv(maxb[i]);
+    maxes[2 * i + 1] = (double)fkey_inv(maxs[i]);
+}
+__global__ void maxr_kernel(const uint64_t* maxr, int nq, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) out[i] = dkey_inv(maxr[i]);
+}
+// merged top candidates [nq][k_stride] -> top_ids / top_scores [nq][MAX_DEPTH]
+__global__ void top_unpack_kernel(const uint64_t* keys, const int64_t* ids, int k_stride, int depth, int64_t* top_ids,
+                                  double* top_scores) {
+    const int qi = blockIdx.x, t = threadIdx.x;
+    if (t >= MAX_DEPTH) return;
+    int64_t id = ID_EMPTY;
+    double sc = -INFINITY;
+    if (t < depth) {
+        const uint64_t k = keys[(size_t)qi * k_stride + t];
+        if (k != KEY_EMPTY) { id = ids[(size_t)qi * k_stride + t]; sc = dkey_inv(k); }
+    }
+    top_ids[qi * MAX_DEPTH + t] = id;
+    top_scores[qi * MAX_DEPTH + t] = sc;
+}
+__global__ void keys_from_scores_kernel(const double* scores, int64_t n, uint64_t* keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = dkey(scores[i]);
+}
+__global__ void fill_empty_kernel(uint64_t* keys, int64_t* ids, int64_t lo, int64_t hi) {
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hi) { keys[i] = KEY_EMPTY; ids[i] = ID_EMPTY; }
+}
+
+}  // namespace
+
+struct ais_engine {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    ais_params p;
+    int64_t first_doc = 0, n_total = -1;
+
+    // index
+    Buf rows;  int64_t n_vec = 0, cap_vec = 0;
+    Buf post_ptr, post_doc, post_tf, idf, kd, doc_len;
+    double avgdl = 0.0;
+    bool has_tf = false;
+    int32_t n_vocab = 0;
+    int64_t n_bm25 = -1, n_post = 0;
+
+    // per-batch work
+    int qt_cap = 0;
+    int64_t ld = 0;
+    Buf sim, bm25, fin, rer, d_q, d_q2, d_qt, maxs_key, maxb_key, maxr_key, maxes_own, maxr_own;
+    Buf top_ids, top_scores, status, rows_own;
+    Buf blk_keys, blk_ids, grp_keys, grp_ids, cand_keys, cand_ids, rest_keys, rest_ids, rest_count;
+    Buf out_ids, out_scores, out_count, out_amb;
+    Buf fs_keys, fs_ids, fs_count;
+    int sel_k_cap = 0, out_topn_cap = 0;
+    int cur_nq = 0;
+    bool cur_prf = false;      // second pass ran for the current batch
+    // pinned host staging
+    float* h_q = nullptr;  QueryTerms* h_qt = nullptr;  float* h_q2 = nullptr;
+    int64_t* h_top_ids = nullptr;  double* h_top_scores = nullptr;
+    int64_t* h_out_ids = nullptr;  double* h_out_scores = nullptr;  int32_t* h_small = nullptr;  // count|status|amb
+    int h_out_cap = 0;
+
+    // stats
+    int64_t scan_launches = 0, kernel_launches = 0, fullsort_fallbacks = 0, bytes_device = 0;
+    bool profiling = false;
+    double scan_ms_total = 0.0;
+    std::vector<cudaEvent_t> ev_pending, ev_free;
+
+    int64_t n() const { return n_vec > 0 ? n_vec : (n_bm25 > 0 ? n_bm25 : 0); }
+    int64_t total() const { return n_total >= 0 ? n_total : n_vec; }
+};
+
+namespace {
+
+int dev_alloc(ais_engine* e, Buf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return AIS_OK;
+    if (b.p) { CK(cudaFree(b.p)); e->bytes_device -= (int64_t)b.cap; b.p = nullptr; b.cap = 0; }
+    CK(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    e->bytes_device += (int64_t)bytes;
+    return AIS_OK;
+}
+void dev_free(ais_engine* e, Buf& b) {
+    if (b.p) { cudaFree(b.p); e->bytes_device -= (int64_t)b.cap; }
+    b.p = nullptr; b.cap = 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int next_pow2_int(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+int sel_blocks(const ais_engine* e) {
+    int64_t g = (e->n() + SEL_MIN_CHUNK - 1) / SEL_MIN_CHUNK;
+    const int64_t cap = 4LL * e->sm_count;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+int merge_groups(int n_lists) { return (n_lists + MERGE_GROUP - 1) / MERGE_GROUP; }
+
+int check_loaded(const ais_engine* e) {
+    if (e->n_bm25 < 0) return fail(AIS_ERR_NOT_LOADED, "BM25 index not loaded (ais_load_bm25)");
+    if (e->n_vec != e->n_bm25)
+        return fail(AIS_ERR_NOT_LOADED, "doc vectors cover %lld docs but the BM25 index covers %lld",
+                    (long long)e->n_vec, (long long)e->n_bm25);
+    return AIS_OK;
+}
+
+int ensure_work(ais_engine* e) {
+    const int qt = next_pow2_int(e->p.max_batch);
+    const int64_t nmax = e->n_vec > e->n_bm25 ? e->n_vec : e->n_bm25;
+    const int64_t ld = ((nmax + 63) / 64) * 64 + 64;
+    if (qt <= e->qt_cap && ld <= e->ld) return AIS_OK;
+    const int q = qt > e->qt_cap ? qt : e->qt_cap;
+    const int64_t l = ld > e->ld ? ld : e->ld;
+    TRY(dev_alloc(e, e->sim, (size_t)q * l * sizeof(float)));
+    TRY(dev_alloc(e, e->rer, (size_t)q * l * sizeof(float)));
+    TRY(dev_alloc(e, e->bm25, (size_t)q * l * sizeof(double)));
+    TRY(dev_alloc(e, e->fin, (size_t)q * l * sizeof(double)));
+    TRY(dev_alloc(e, e->d_q, (size_t)q * DIM * sizeof(float)));
+    TRY(dev_alloc(e, e->d_q2, (size_t)q * DIM * sizeof(float)));
+    TRY(dev_alloc(e, e->d_qt, (size_t)q * sizeof(QueryTerms)));
+    TRY(dev_alloc(e, e->maxs_key, (size_t)q * sizeof(uint32_t)));
+    TRY(dev_alloc(e, e->maxb_key, (size_t)q * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->maxr_key, (size_t)q * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->maxes_own, (size_t)q * 2 * sizeof(double)));
+    TRY(dev_alloc(e, e->maxr_own, (size_t)q * sizeof(double)));
+    TRY(dev_alloc(e, e->top_ids, (size_t)q * MAX_DEPTH * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->top_scores, (size_t)q * MAX_DEPTH * sizeof(double)));
+    TRY(dev_alloc(e, e->status, (size_t)q * sizeof(int32_t)));
+    TRY(dev_alloc(e, e->rows_own, (size_t)q * MAX_DEPTH * DIM * sizeof(float)));
+    TRY(dev_alloc(e, e->out_count, (size_t)q * sizeof(int32_t)));
+    TRY(dev_alloc(e, e->out_amb, (size_t)q * sizeof(int32_t)));
+    if (q > e->qt_cap) {
+        if (e->h_q) { cudaFreeHost(e->h_q); cudaFreeHost(e->h_qt); cudaFreeHost(e->h_q2); cudaFreeHost(e->h_top_ids);
+                      cudaFreeHost(e->h_top_scores); cudaFreeHost(e->h_small); }
+        CK(cudaMallocHost((void**)&e->h_q, (size_t)q * DIM * sizeof(float)));
+        CK(cudaMallocHost((void**)&e->h_q2, (size_t)q * DIM * sizeof(float)));
+        CK(cudaMallocHost((void**)&e->h_qt, (size_t)q * sizeof(QueryTerms)));
+        CK(cudaMallocHost((void**)&e->h_top_ids, (size_t)q * MAX_DEPTH * sizeof(int64_t)));
+        CK(cudaMallocHost((void**)&e->h_top_scores, (size_t)q * MAX_DEPTH * sizeof(double)));
+        CK(cudaMallocHost((void**)&e->h_small, (size_t)q * 3 * sizeof(int32_t)));
+        e->sel_k_cap = 0;       // candidate buffers are sized per query too
+        e->out_topn_cap = 0;
+    }
+    e->qt_cap = q;
+    e->ld = l;
+    return AIS_OK;
+}
+
+int ensure_sel(ais_engine* e, int k) {
+    if (k <= e->sel_k_cap) return AIS_OK;
+    const size_t q = (size_t)e->qt_cap;
+    const size_t G = (size_t)4 * e->sm_count;
+    const size_t ng = (size_t)merge_groups((int)G) + 64;
+    TRY(dev_alloc(e, e->blk_keys, q * G * k * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->blk_ids, q * G * k * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->grp_keys, q * ng * k * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->grp_ids, q * ng * k * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->cand_keys, q * k * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->cand_ids, q * k * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->rest_keys, q * k * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->rest_ids, q * k * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->rest_count, q * sizeof(int32_t)));
+    e->sel_k_cap = k;
+    return AIS_OK;
+}
+
+int ensure_out(ais_engine* e, int topn) {
+    if (topn <= e->out_topn_cap) return AIS_OK;
+    const size_t q = (size_t)e->qt_cap;
+    TRY(dev_alloc(e, e->out_ids, q * topn * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->out_scores, q * topn * sizeof(double)));
+    if (e->h_out_ids) { cudaFreeHost(e->h_out_ids); cudaFreeHost(e->h_out_scores); }
+    CK(cudaMallocHost((void**)&e->h_out_ids, q * topn * sizeof(int64_t)));
+    CK(cudaMallocHost((void**)&e->h_out_scores, q * topn * sizeof(double)));
+    e->out_topn_cap = topn;
+    return AIS_OK;
+}
+
+#define LAUNCHED(e) do { (e)->kernel_launches++; CK(cudaGetLastError()); } while (0)
+
+CombineParams combine_params(const ais_engine* e) {
+    CombineParams cp;
+    cp.wb = e->p.bm25_weight;
+    cp.wd = (float)e->p.doc2vec_weight;
+    cp.wo = e->p.original_score_weight;
+    cp.wr = (float)e->p.reranked_score_weight;
+    return cp;
+}
+
+template <int QT>
+int launch_scan_t(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
+    const int64_t n_tiles = (e->n_vec + TILE_ROWS - 1) / TILE_ROWS;
+    int grid = (int)(n_tiles < e->sm_count ? n_tiles : e->sm_count);
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (e->profiling) {
+        for (cudaEvent_t* ev : {&a, &b}) {
+            if (!e->ev_free.empty()) { *ev = e->ev_free.back(); e->ev_free.pop_back(); }
+            else CK(cudaEventCreate(ev));
+        }
+        CK(cudaEventRecord(a, e->stream));
+    }
+    scan_kernel<QT><<<grid, SCAN_THREADS, scan_smem_bytes<QT>(), e->stream>>>(
+        e->rows.as<float>(), e->n_vec, d_q, out, e->ld, max_keys, nq, 1);
+    LAUNCHED(e);
+    e->scan_launches++;
+    if (e->profiling) {
+        CK(cudaEventRecord(b, e->stream));
+        e->ev_pending.push_back(a);
+        e->ev_pending.push_back(b);
+    }
+    return AIS_OK;
+}
+
+int launch_scan(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
+    if (e->n_vec == 0) return AIS_OK;
+    if (nq <= 1) return launch_scan_t<1>(e, d_q, nq, out, max_keys);
+    if (nq <= 2) return launch_scan_t<2>(e, d_q, nq, out, max_keys);
+    if (nq <= 4) return launch_scan_t<4>(e, d_q, nq, out, max_keys);
+    if (nq <= 8) return launch_scan_t<8>(e, d_q, nq, out, max_keys);
+    return launch_scan_t<16>(e, d_q, nq, out, max_keys);
+}
+
+int set_scan_attrs() {
+    CK(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<1>()));
+    CK(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<2>()));
+    CK(cudaFuncSetAttribute(scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<4>()));
+    CK(cudaFuncSetAttribute(scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<8>()));
+    CK(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<16>()));
+    return AIS_OK;
+}
+
+int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bool with_terms) {
+    for (int i = 0; i < nq; ++i) {
+        if (with_vec) {
+            if (!qs[i].vec) return fail(AIS_ERR_INVALID, "query %d: vec is NULL", i);
+            memcpy(e->h_q + (size_t)i * DIM, qs[i].vec, DIM * sizeof(float));
+        }
+        if (with_terms) {
+            if (qs[i].n_terms < 0 || qs[i].n_terms > MAX_TERMS)
+                return fail(AIS_ERR_INVALID, "query %d: n_terms %d outside [0, %d]", i, qs[i].n_terms, MAX_TERMS);
+            QueryTerms& t = e->h_qt[i];
+            t.n_terms = qs[i].n_terms;
+            for (int j = 0; j < qs[i].n_terms; ++j) { t.term[j] = qs[i].term_ids[j]; t.weight[j] = qs[i].weights[j]; }
+        }
+    }
+    if (with_vec) {
+        const int padded = next_pow2_int(nq);
+        for (int i = nq; i < padded; ++i) memset(e->h_q + (size_t)i * DIM, 0, DIM * sizeof(float));
+        CK(cudaMemcpyAsync(e->d_q.p, e->h_q, (size_t)padded * DIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+    if (with_terms)
+        CK(cudaMemcpyAsync(e->d_qt.p, e->h_qt, (size_t)nq * sizeof(QueryTerms), cudaMemcpyHostToDevice, e->stream));
+    return AIS_OK;
+}
+
+int launch_bm25(ais_engine* e, int nq) {
+    if (e->n_bm25 <= 0) return AIS_OK;
+    dim3 grid((unsigned)((e->n_bm25 + BM25_TILE - 1) / BM25_TILE), (unsigned)nq);
+    bm25_kernel<<<grid, BM25_THREADS, 0, e->stream>>>(
+        e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->has_tf ? e->post_tf.as<int32_t>() : nullptr,
+        e->idf.as<double>(), e->kd.as<double>(), e->n_bm25, e->n_vocab, e->d_qt.as<QueryTerms>(), e->p.require_magic,
+        e->p.k1 + 1.0, e->bm25.as<double>(), e->ld, e->maxb_key.as<uint64_t>());
+    LAUNCHED(e);
+    return AIS_OK;
+}
+
+// two-level merge of candidate lists into out[nq][k_out] (sorted best first, KEY_EMPTY padded)
+int merge_lists(ais_engine* e, const uint64_t* keys, const int64_t* ids, int n_lists, int64_t list_stride,
+                int64_t q_stride, int k_in, int k_out, int nq, uint64_t* out_keys, int64_t* out_ids, int32_t* out_count) {
+    if (n_lists > 2 * MERGE_GROUP) {
+        const int ng = merge_groups(n_lists);
+        if ((size_t)e->qt_cap * ng * k_out * sizeof(uint64_t) > e->grp_keys.cap)
+            return fail(AIS_ERR_INVALID, "too many candidate lists to merge (%d)", n_lists);
+        merge_kernel<<<dim3(ng, nq), SEL_THREADS, 0, e->stream>>>(keys, ids, n_lists, MERGE_GROUP, list_stride, q_stride,
+                                                                 k_in, k_out, e->grp_keys.as<uint64_t>(),
+                                                                 e->grp_ids.as<int64_t>(), k_out, nullptr);
+        LAUNCHED(e);
+        merge_kernel<<<dim3(1, nq), SEL_THREADS, 0, e->stream>>>(e->grp_keys.as<uint64_t>(), e->grp_ids.as<int64_t>(), ng, ng,
+                                                                k_out, (int64_t)ng * k_out, k_out, k_out, out_keys, out_ids,
+                                                                k_out, out_count);
+        LAUNCHED(e);
+    } else {
+        merge_kernel<<<dim3(1, nq), SEL_THREADS, 0, e->stream>>>(keys, ids, n_lists, n_lists, list_stride, q_stride, k_in,
+                                                                k_out, out_keys, out_ids, k_out, out_count);
+        LAUNCHED(e);
+    }
+    return AIS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
+    TRY(check_loaded(e));
+    TRY(ensure_work(e));
+    if (nq < 1 || nq > e->p.max_batch) return fail(AIS_ERR_INVALID, "nq %d outside [1, max_batch=%d]", nq, e->p.max_batch);
+    TRY(upload_queries(e, qs, nq, true, true));
+    init_keys_kernel<<<1, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
+                                             e->maxr_key.as<uint64_t>(), e->status.as<int32_t>(), nq, 1);
+    LAUNCHED(e);
+    TRY(launch_bm25(e, nq));
+    TRY(launch_scan(e, e->d_q.as<float>(), nq, e->sim.as<float>(), e->maxs_key.as<uint32_t>()));
+    maxes_kernel<<<1, 64, 0, e->stream>>>(e->maxb_key.as<uint64_t>(), e->maxs_key.as<uint32_t>(), nq, d_maxes);
+    LAUNCHED(e);
+    e->cur_nq = nq;
+    e->cur_prf = false;
+    return AIS_OK;
+}
+
+// from_final: select straight from e->fin (ais_rerank); else combine sim + bm25 first
+int do_combine(ais_engine* e, int nq, const double* d_maxes, int k, uint64_t* d_keys, int64_t* d_ids, bool from_final) {
+    if (k < 1 || k > SEL_KMAX) return fail(AIS_ERR_INVALID, "k %d outside [1, %d]", k, SEL_KMAX);
+    TRY(ensure_sel(e, k));
+    const int G = sel_blocks(e);
+    if (from_final)
+        final_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(e->fin.as<double>(), e->n(), e->ld, e->first_doc, k,
+                                                                       e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>());
+    else
+        combine_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
+            e->sim.as<float>(), e->bm25.as<double>(), e->fin.as<double>(), e->n(), e->ld, d_maxes, combine_params(e),
+            e->first_doc, k, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>());
+    LAUNCHED(e);
+    return merge_lists(e, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), G, k, (int64_t)G * k, k, k, nq, d_keys,
+                       d_ids, nullptr);
+}
+
+int do_top(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys, const int64_t* d_ids, int64_t* out_top_ids,
+           double* out_top_scores, float* d_rows) {
+    const int depth = e->p.prf_depth;
+    TRY(ensure_sel(e, k > depth ? k : depth));
+    const uint64_t* mk = d_keys;
+    const int64_t* mi = d_ids;
+    int stride = k;
+    if (n_lists > 1) {
+        TRY(merge_lists(e, d_keys, d_ids, n_lists, (int64_t)nq * k, k, k, depth, nq, e->rest_keys.as<uint64_t>(),
+                        e->rest_ids.as<int64_t>(), nullptr));
+        mk = e->rest_keys.as<uint64_t>();
+        mi = e->rest_ids.as<int64_t>();
+        stride = depth;
+    } else if (k < depth) {
+        return fail(AIS_ERR_INVALID, "stage_top: k %d < prf_depth %d", k, depth);
+    }
+    top_unpack_kernel<<<nq, 32, 0, e->stream>>>(mk, mi, stride, depth, e->top_ids.as<int64_t>(), e->top_scores.as<double>());
+    LAUNCHED(e);
+    if (d_rows) {
+        gather_top_rows_kernel<<<dim3(depth, nq), 128, 0, e->stream>>>(e->rows.as<float>(), e->n(), e->first_doc,
+                                                                      e->top_ids.as<int64_t>(), depth, d_rows);
+        LAUNCHED(e);
+    }
+    if (out_top_ids || out_top_scores) {
+        CK(cudaMemcpyAsync(e->h_top_ids, e->top_ids.p, (size_t)nq * MAX_DEPTH * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_top_scores, e->top_scores.p, (size_t)nq * MAX_DEPTH * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        for (int q = 0; q < nq; ++q)
+            for (int t = 0; t < depth; ++t) {
+                if (out_top_ids) out_top_ids[q * depth + t] = e->h_top_ids[q * MAX_DEPTH + t];
+                if (out_top_scores) out_top_scores[q * depth + t] = e->h_top_scores[q * MAX_DEPTH + t];
+            }
+    }
+    return AIS_OK;
+}
+
+int do_requery_select(ais_engine* e, int nq, int k, uint64_t* d_keys, int64_t* d_ids) {
+    if (k < 1 || k > SEL_KMAX) return fail(AIS_ERR_INVALID, "k %d outside [1, %d]", k, SEL_KMAX);
+    TRY(ensure_sel(e, k));
+    const int G = sel_blocks(e);
+    // the max is re-accumulated (idempotent under atomicMax)
+    rerank_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
+        e->fin.as<double>(), e->rer.as<float>(), e->n(), e->ld, combine_params(e), e->first_doc, e->top_ids.as<int64_t>(),
+        e->p.prf_depth, k, e->maxr_key.as<uint64_t>(), e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>());
+    LAUNCHED(e);
+    return merge_lists(e, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), G, k, (int64_t)G * k, k, k, nq, d_keys,
+                       d_ids, nullptr);
+}
+
+int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows, int prf_mode, int k, double* d_max_r,
+               uint64_t* d_keys, int64_t* d_ids) {
+    const int depth = e->p.prf_depth;
+    if (q2_host) {
+        const int padded = next_pow2_int(nq);
+        memcpy(e->h_q2, q2_host, (size_t)nq * DIM * sizeof(float));
+        for (int i = nq; i < padded; ++i) memset(e->h_q2 + (size_t)i * DIM, 0, DIM * sizeof(float));
+        CK(cudaMemcpyAsync(e->d_q2.p, e->h_q2, (size_t)padded * DIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    } else {
+        if (!d_rows) return fail(AIS_ERR_INVALID, "stage_requery: neither q2 nor d_rows given");
+        if (prf_mode != AIS_PRF_STORED_ROWS && prf_mode != AIS_PRF_STORED_ROWS_FULL)
+            return fail(AIS_ERR_INVALID, "stage_requery: device re-query needs a STORED_ROWS prf_mode");
+        const int padded = next_pow2_int(nq);
+        if (padded > nq)
+            CK(cudaMemsetAsync(e->d_q2.as<float>() + (size_t)nq * DIM, 0, (size_t)(padded - nq) * DIM * sizeof(float), e->stream));
+        prf_query_kernel<<<nq, 320, 0, e->stream>>>(d_rows, e->top_scores.as<double>(), depth,
+                                                   prf_mode == AIS_PRF_STORED_ROWS ? 1 : 0, e->d_q2.as<float>(),
+                                                   e->status.as<int32_t>());
+        LAUNCHED(e);
+    }
+    init_keys_kernel<<<1, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
+                                             e->maxr_key.as<uint64_t>(), e->status.as<int32_t>(), nq, 2);
+    LAUNCHED(e);
+    TRY(launch_scan(e, e->d_q2.as<float>(), nq, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
+    TRY(do_requery_select(e, nq, k, d_keys, d_ids));
+    maxr_kernel<<<1, 64, 0, e->stream>>>(e->maxr_key.as<uint64_t>(), nq, d_max_r);
+    LAUNCHED(e);
+    e->cur_prf = true;
+    return AIS_OK;
+}
+
+int copy_results(ais_engine* e, int nq, int topn, int64_t* out_ids, double* out_scores, int32_t* out_counts,
+                 int32_t* out_status, int32_t* out_amb) {
+    CK(cudaMemcpyAsync(e->h_out_ids, e->out_ids.p, (size_t)nq * topn * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_out_scores, e->out_scores.p, (size_t)nq * topn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_small, e->out_count.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_small + e->qt_cap, e->status.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_small + 2 * e->qt_cap, e->out_amb.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int q = 0; q < nq; ++q) {
+        const int st = e->h_small[e->qt_cap + q];
+        const int cnt = st == AIS_Q_OK ? e->h_small[q] : 0;
+        if (out_counts) out_counts[q] = cnt;
+        if (out_status) out_status[q] = st;
+        if (out_amb) out_amb[q] = st == AIS_Q_OK ? e->h_small[2 * e->qt_cap + q] : 0;
+        if (out_ids) memcpy(out_ids + (size_t)q * topn, e->h_out_ids + (size_t)q * topn, (size_t)cnt * sizeof(int64_t));
+        if (out_scores) memcpy(out_scores + (size_t)q * topn, e->h_out_scores + (size_t)q * topn, (size_t)cnt * sizeof(double));
+    }
+    return AIS_OK;
+}
+
+// d_max_r == NULL: the no-PRF branch (webui.py:247-253) - candidates are sorted finals, no pinned docs
+int do_finish(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys, const int64_t* d_ids, const double* d_max_r,
+              int topn, int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status, int32_t* out_amb) {
+    if (topn < 1) return fail(AIS_ERR_INVALID, "topn must be >= 1");
+    TRY(ensure_sel(e, k));
+    TRY(ensure_out(e, topn));
+    TRY(merge_lists(e, d_keys, d_ids, n_lists, (int64_t)nq * k, k, k, k, nq, e->rest_keys.as<uint64_t>(),
+                    e->rest_ids.as<int64_t>(), e->rest_count.as<int32_t>()));
+    TailParams tp;
+    tp.thresh = e->p.diff_filter_thresh;
+    tp.topn = topn;
+    tp.depth = d_max_r ? e->p.prf_depth : 0;
+    tp.normalize = d_max_r ? 1 : 0;
+    tp.n_total = e->total();
+    tail_kernel<<<nq, SEL_THREADS, 0, e->stream>>>(e->rest_keys.as<uint64_t>(), e->rest_ids.as<int64_t>(), k,
+                                                  e->rest_count.as<int32_t>(), nullptr, e->top_ids.as<int64_t>(), d_max_r, tp,
+                                                  e->out_ids.as<int64_t>(), e->out_scores.as<double>(),
+                                                  e->out_count.as<int32_t>(), e->out_amb.as<int32_t>());
+    LAUNCHED(e);
+    return copy_results(e, nq, topn, out_ids, out_scores, out_counts, out_status, out_amb);
+}
+
+int64_t sort_capacity(int64_t n) {
+    int64_t p = GS_TILE;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// sort n_pad (power of two >= GS_TILE) entries best-first
+int bitonic_sort(ais_engine* e, uint64_t* keys, int64_t* ids, int64_t n_pad) {
+    const unsigned blocks = (unsigned)(n_pad / GS_TILE);
+    bitonic_local_kernel<<<blocks, GS_THREADS, 0, e->stream>>>(keys, ids, n_pad, 2ull, (unsigned long long)GS_TILE);
+    LAUNCHED(e);
+    for (unsigned long long size = 2ull * GS_TILE; size <= (unsigned long long)n_pad; size <<= 1) {
+        for (unsigned long long stride = size >> 1; stride >= (unsigned long long)GS_TILE; stride >>= 1) {
+            bitonic_global_kernel<<<(unsigned)((n_pad / 2 + 255) / 256), 256, 0, e->stream>>>(keys, ids, n_pad, size, stride);
+            LAUNCHED(e);
+        }
+        bitonic_local_kernel<<<blocks, GS_THREADS, 0, e->stream>>>(keys, ids, n_pad, size, size);
+        LAUNCHED(e);
+    }
+    return AIS_OK;
+}
+
+// write this shard's keys of query qi (pass 2: R, seeds blanked; pass 1: finals) into caller arrays [n_local]
+int do_export_keys(ais_engine* e, int qi, int second_pass, uint64_t* d_keys, int64_t* d_ids) {
+    if (e->n() == 0) return AIS_OK;
+    fill_keys_kernel<<<(unsigned)((e->n() + 255) / 256), 256, 0, e->stream>>>(
+        e->fin.as<double>() + (size_t)qi * e->ld, e->rer.as<float>() + (size_t)qi * e->ld, e->n(), combine_params(e),
+        second_pass ? 1 : 0, e->first_doc, e->top_ids.as<int64_t>() + (size_t)qi * MAX_DEPTH, second_pass ? e->p.prf_depth : 0,
+        d_keys, d_ids, e->n());
+    LAUNCHED(e);
+    return AIS_OK;
+}
+
+// full sort of n_entries keys (all shards' exports, concatenated by the caller into arrays of
+// ais_sort_capacity(n_entries) slots) and the exact tail for query qi
+int do_sort_finish(ais_engine* e, int qi, uint64_t* d_keys, int64_t* d_ids, int64_t n_entries, const double* d_max_r, int topn,
+                   int64_t* out_ids, double* out_scores, int32_t* out_count, int32_t* out_status) {
+    TRY(ensure_out(e, topn));
+    TRY(dev_alloc(e, e->fs_count, sizeof(int64_t) * 2));
+    const int64_t n_pad = sort_capacity(n_entries);
+    if (n_pad > n_entries) {
+        fill_empty_kernel<<<(unsigned)((n_pad - n_entries + 255) / 256), 256, 0, e->stream>>>(d_keys, d_ids, n_entries, n_pad);
+        LAUNCHED(e);
+    }
+    TRY(bitonic_sort(e, d_keys, d_ids, n_pad));
+    CK(cudaMemsetAsync(e->fs_count.p, 0, sizeof(int64_t), e->stream));
+    count_live_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, e->stream>>>(d_keys, n_pad, e->fs_count.as<int64_t>());
+    LAUNCHED(e);
+    TailParams tp;
+    tp.thresh = e->p.diff_filter_thresh;
+    tp.topn = topn;
+    tp.depth = d_max_r ? e->p.prf_depth : 0;
+    tp.normalize = d_max_r ? 1 : 0;
+    tp.n_total = e->total();
+    // single-query launch: offset every per-query array to qi
+    tail_kernel<<<1, SEL_THREADS, 0, e->stream>>>(d_keys, d_ids, 0, nullptr, e->fs_count.as<int64_t>(),
+                                                 e->top_ids.as<int64_t>() + (size_t)qi * MAX_DEPTH,
+                                                 d_max_r ? d_max_r + qi : nullptr, tp, e->out_ids.as<int64_t>(),
+                                                 e->out_scores.as<double>(), e->out_count.as<int32_t>(),
+                                                 e->out_amb.as<int32_t>());
+    LAUNCHED(e);
+    e->fullsort_fallbacks++;
+    CK(cudaMemcpyAsync(e->h_out_ids, e->out_ids.p, (size_t)topn * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_out_scores, e->out_scores.p, (size_t)topn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_small, e->out_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_small + 1, e->status.as<int32_t>() + qi, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const int st = e->h_small[1];
+    const int cnt = st == AIS_Q_OK ? e->h_small[0] : 0;
+    if (out_count) *out_count = cnt;
+    if (out_status) *out_status = st;
+    if (out_ids) memcpy(out_ids, e->h_out_ids, (size_t)cnt * sizeof(int64_t));
+    if (out_scores) memcpy(out_scores, e->h_out_scores, (size_t)cnt * sizeof(double));
+    return AIS_OK;
+}
+
+// numpy's float64 pairwise sum of < 128 items (np.average's wgt.sum())
+double np_sum_host(const double* a, int n) {
+    if (n < 8) { double r = 0.0; for (int i = 0; i < n; ++i) r += a[i]; return r; }
+    double r[8];
+    for (int k = 0; k < 8; ++k) r[k] = a[k];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+
+// One batch on one GPU.  qs == NULL: finals are already in e->fin (ais_rerank).
+int run_batch(ais_engine* e, const ais_query* qs, int q_index0, int nq, int topn, int prf_mode, ais_infer_cb cb, void* ctx,
+              int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status) {
+    const int depth = e->p.prf_depth;
+    double* maxes = e->maxes_own.as<double>();
+    if (qs) TRY(do_score(e, qs, nq, maxes));
+    const bool prf = prf_mode != AIS_PRF_OFF && e->total() > depth;     // webui.py:193 `len(sims) > 10`
+    std::vector<int32_t> amb(nq, 0), status(nq, 0);
+    {   // size the candidate buffers BEFORE their pointers are taken below
+        int kk = topn + 1 < SEL_KMAX ? topn + 1 : SEL_KMAX;
+        if (kk < depth) kk = depth;
+        TRY(ensure_sel(e, kk));
+    }
+
+    if (!prf) {
+        int k = topn + 1 < SEL_KMAX ? topn + 1 : SEL_KMAX;
+        for (;;) {
+            TRY(do_combine(e, nq, maxes, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), qs == nullptr));
+            TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), nullptr, topn, out_ids,
+                          out_scores, out_counts, out_status, amb.data()));
+            bool any = false;
+            for (int q = 0; q < nq; ++q) any = any || amb[q];
+            if (!any || k == SEL_KMAX) break;
+            k = SEL_KMAX;
+            TRY(ensure_sel(e, k));
+        }
+    } else {
+        TRY(do_combine(e, nq, maxes, depth, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), qs == nullptr));
+        const bool host_q2 = prf_mode == AIS_PRF_CALLBACK;
+        std::vector<int64_t> top_ids;
+        std::vector<double> top_scores;
+        std::vector<float> q2;
+        if (host_q2) {
+            if (!cb) return fail(AIS_ERR_INVALID, "AIS_PRF_CALLBACK needs a callback");
+            top_ids.resize((size_t)nq * depth);
+            top_scores.resize((size_t)nq * depth);
+            q2.assign((size_t)nq * DIM, 0.0f);
+        }
+        TRY(do_top(e, nq, 1, depth, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), host_q2 ? top_ids.data() : nullptr,
+                   host_q2 ? top_scores.data() : nullptr, host_q2 ? nullptr : e->rows_own.as<float>()));
+        if (host_q2) {
+            bool any_bad = false;
+            for (int q = 0; q < nq; ++q) {
+                const double* w = &top_scores[(size_t)q * depth];
+                bool bad = false;
+                for (int t = 0; t < depth; ++t) bad = bad || !isfinite(w[t]);
+                if (bad) status[q] = AIS_Q_NAN_WEIGHTS;                       // webui.py:200-203
+                else if (np_sum_host(w, depth) == 0.0) status[q] = AIS_Q_ZERO_WEIGHT_SUM;
+                else if (cb(ctx, q_index0 + q, &top_ids[(size_t)q * depth], w, depth, &q2[(size_t)q * DIM]) != 0) {
+                    status[q] = AIS_Q_CALLBACK_FAILED;
+                    memset(&q2[(size_t)q * DIM], 0, DIM * sizeof(float));
+                }
+                any_bad = any_bad || status[q] != 0;
+            }
+            if (any_bad)
+                CK(cudaMemcpyAsync(e->status.p, status.data(), (size_t)nq * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        }
+        int k = topn + 1 - depth;
+        if (k < 1) k = 1;
+        if (k > SEL_KMAX) k = SEL_KMAX;
+        double* maxr = e->maxr_own.as<double>();
+        TRY(do_requery(e, nq, host_q2 ? q2.data() : nullptr, host_q2 ? nullptr : e->rows_own.as<float>(), prf_mode, k, maxr,
+                       e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>()));
+        for (;;) {
+            TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), maxr, topn, out_ids, out_scores,
+                          out_counts, out_status, amb.data()));
+            bool any = false;
+            for (int q = 0; q < nq; ++q) any = any || amb[q];
+            if (!any || k == SEL_KMAX) break;
+            k = SEL_KMAX;
+            TRY(ensure_sel(e, k));
+            TRY(do_requery_select(e, nq, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>()));
+        }
+    }
+    // exact fallback: the filter outcome depends on scores beyond the SEL_KMAX best -> sort everything
+    for (int q = 0; q < nq; ++q) {
+        if (!amb[q]) continue;
+        const int64_t cap = sort_capacity(e->n());
+        TRY(dev_alloc(e, e->fs_keys, (size_t)cap * sizeof(uint64_t)));
+        TRY(dev_alloc(e, e->fs_ids, (size_t)cap * sizeof(int64_t)));
+        TRY(do_export_keys(e, q, prf ? 1 : 0, e->fs_keys.as<uint64_t>(), e->fs_ids.as<int64_t>()));
+        TRY(do_sort_finish(e, q, e->fs_keys.as<uint64_t>(), e->fs_ids.as<int64_t>(), e->n(), prf ? e->maxr_own.as<double>() : nullptr,
+                           topn, out_ids ? out_ids + (size_t)q * topn : nullptr, out_scores ? out_scores + (size_t)q * topn : nullptr,
+                           out_counts ? out_counts + q : nullptr, out_status ? out_status + q : nullptr));
+    }
+    return AIS_OK;
+}
+
+int need_whole_index(const ais_engine* e) {
+    if (e->total() != e->n() || e->first_doc != 0)
+        return fail(AIS_ERR_INVALID, "this engine holds a shard (%lld of %lld docs): drive it through the ais_stage_* calls",
+                    (long long)e->n(), (long long)e->total());
+    return AIS_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* ais_last_error(void) { return g_err; }
+int ais_abi_version(void) { return AIS_ABI_VERSION; }
+int ais_max_select_k(void) { return SEL_KMAX; }
+int64_t ais_sort_capacity(int64_t n_entries) { return sort_capacity(n_entries); }
+
+void ais_default_params(ais_params* p) {
+    if (!p) return;
+    p->k1 = 1.5;
+    p->b = 0.75;
+    p->bm25_weight = 0.5;
+    p->doc2vec_weight = 0.5;
+    p->original_score_weight = 0.7;
+    p->reranked_score_weight = 0.3;
+    p->diff_filter_thresh = 1e-6;
+    p->require_magic = 1000.0;
+    p->prf_depth = 10;
+    p->max_batch = 1;
+}
+
+static int validate_params(const ais_params* p) {
+    if (p->prf_depth < 1 || p->prf_depth > MAX_DEPTH) return fail(AIS_ERR_INVALID, "prf_depth %d outside [1, %d]", p->prf_depth, MAX_DEPTH);
+    if (p->max_batch < 1 || p->max_batch > MAX_QT) return fail(AIS_ERR_INVALID, "max_batch %d outside [1, %d]", p->max_batch, MAX_QT);
+    return AIS_OK;
+}
+
+int ais_create(ais_engine** out, int device_id, const ais_params* p) {
+    if (!out) return fail(AIS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return fail(AIS_ERR_CUDA, "no CUDA device available (%s): the ais_b200 engine has no CPU path", cudaGetErrorString(ce));
+    if (device_id < 0 || device_id >= count) return fail(AIS_ERR_INVALID, "device_id %d outside [0, %d)", device_id, count);
+    ais_params pp;
+    ais_default_params(&pp);
+    if (p) pp = *p;
+    TRY(validate_params(&pp));
+    DeviceGuard g(device_id);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major < 10)
+        return fail(AIS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device_id, prop.major, prop.minor);
+    ais_engine* e = new ais_engine();
+    e->device = device_id;
+    e->sm_count = prop.multiProcessorCount;
+    e->p = pp;
+    cudaError_t se = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) { delete e; return fail(AIS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
+    e->stream = e->own_stream;
+    int s = set_scan_attrs();
+    if (s != AIS_OK) { cudaStreamDestroy(e->own_stream); delete e; return s; }
+    *out = e;
+    return AIS_OK;
+}
+
+int ais_destroy(ais_engine* e) {
+    if (!e) return AIS_OK;
+    DeviceGuard g(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->doc_len, &e->sim, &e->bm25, &e->fin,
+                   &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
+                   &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
+                   &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
+                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count})
+        dev_free(e, *b);
+    for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,
+                    (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small})
+        if (h) cudaFreeHost(h);
+    for (cudaEvent_t ev : e->ev_pending) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_free) cudaEventDestroy(ev);
+    cudaStreamDestroy(e->own_stream);
+    delete e;
+    return AIS_OK;
+}
+
+int ais_set_params(ais_engine* e, const ais_params* p) {
+    if (!e || !p) return fail(AIS_ERR_INVALID, "NULL argument");
+    TRY(validate_params(p));
+    DeviceGuard g(e->device);
+    const bool kd_stale = (p->k1 != e->p.k1 || p->b != e->p.b) && e->n_bm25 > 0;
+    e->p = *p;
+    if (kd_stale) {
+        kd_kernel<<<(unsigned)((e->n_bm25 + 255) / 256), 256, 0, e->stream>>>(e->doc_len.as<int64_t>(), e->n_bm25, e->avgdl, e->p.k1,
+                                                                             e->p.b, 1.0 - e->p.b, e->kd.as<double>());
+        LAUNCHED(e);
+    }
+    return AIS_OK;
+}
+
+int ais_set_stream(ais_engine* e, void* cuda_stream) {
+    if (!e) return fail(AIS_ERR_INVALID, "NULL engine");
+    DeviceGuard g(e->device);
+    CK(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return AIS_OK;
+}
+
+int ais_set_shard(ais_engine* e, int64_t first_doc_id, int64_t n_total_docs) {
+    if (!e) return fail(AIS_ERR_INVALID, "NULL engine");
+    if (first_doc_id < 0 || n_total_docs < 0) return fail(AIS_ERR_INVALID, "negative shard bounds");
+    e->first_doc = first_doc_id;
+    e->n_total = n_total_docs;
+    return AIS_OK;
+}
+
+int ais_reserve_docs(ais_engine* e, int64_t n_docs) {
+    if (!e || n_docs < 0) return fail(AIS_ERR_INVALID, "bad argument");
+    DeviceGuard g(e->device);
+    if (n_docs <= e->cap_vec) return AIS_OK;
+    Buf nb;
+    TRY(dev_alloc(e, nb, (size_t)n_docs * ROW_BYTES));
+    if (e->n_vec > 0) CK(cudaMemcpyAsync(nb.p, e->rows.p, (size_t)e->n_vec * ROW_BYTES, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    dev_free(e, e->rows);
+    e->rows = nb;
+    e->cap_vec = n_docs;
+    return AIS_OK;
+}
+
+int ais_load_vectors(ais_engine* e, const float* rows, int64_t n, int32_t dim, int64_t first_row) {
+    if (!e || (!rows && n > 0) || n < 0 || first_row < 0) return fail(AIS_ERR_INVALID, "bad argument");
+    if (dim != DIM) return fail(AIS_ERR_UNSUPPORTED, "vector dimension %d: only %d (genmodel.py:16 VECTOR_LENGTH) is built", dim, DIM);
+    if (first_row > e->n_vec) return fail(AIS_ERR_INVALID, "first_row %lld leaves a gap after %lld loaded rows", (long long)first_row, (long long)e->n_vec);
+    DeviceGuard g(e->device);
+    if (first_row + n > e->cap_vec) {
+        int64_t want = e->cap_vec + e->cap_vec / 2;
+        if (want < first_row + n) want = first_row + n;
+        TRY(ais_reserve_docs(e, want));
+    }
+    if (n > 0)
+        CK(cudaMemcpyAsync(e->rows.as<float>() + (size_t)first_row * DIM, rows, (size_t)n * ROW_BYTES, cudaMemcpyDefault, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (first_row + n > e->n_vec) e->n_vec = first_row + n;
+    return AIS_OK;
+}
+
+int ais_vectors_device_ptr(ais_engine* e, int64_t n_docs, float** out_rows) {
+    if (!e || !out_rows || n_docs < 0) return fail(AIS_ERR_INVALID, "bad argument");
+    TRY(ais_reserve_docs(e, n_docs));
+    e->n_vec = n_docs;
+    *out_rows = e->rows.as<float>();
+    return AIS_OK;
+}
+
+int ais_load_bm25(ais_engine* e, const int64_t* post_ptr, const int32_t* post_doc, const int32_t* post_tf, int32_t n_terms,
+                  int64_t n_docs, const double* idf, const int64_t* doc_len, double avgdl) {
+    if (!e || !post_ptr || !idf || (!doc_len && n_docs > 0) || n_terms < 0 || n_docs < 0) return fail(AIS_ERR_INVALID, "bad argument");
+    if (n_docs >= (1LL << 31)) return fail(AIS_ERR_UNSUPPORTED, "a shard holds at most 2^31-1 docs (int32 local doc ids)");
+    DeviceGuard g(e->device);
+    TRY(dev_alloc(e, e->post_ptr, (size_t)(n_terms + 1) * sizeof(int64_t)));
+    CK(cudaMemcpyAsync(e->post_ptr.p, post_ptr, (size_t)(n_terms + 1) * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+    int64_t n_post = 0;
+    CK(cudaMemcpyAsync(&n_post, (const char*)e->post_ptr.p + (size_t)n_terms * sizeof(int64_t), sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (n_post < 0) return fail(AIS_ERR_INVALID, "post_ptr[n_terms] is negative");
+    if (n_post > 0 && !post_doc) return fail(AIS_ERR_INVALID, "post_doc is NULL");
+    TRY(dev_alloc(e, e->post_doc, (size_t)n_post * sizeof(int32_t)));
+    if (n_post > 0) CK(cudaMemcpyAsync(e->post_doc.p, post_doc, (size_t)n_post * sizeof(int32_t), cudaMemcpyDefault, e->stream));
+    e->has_tf = post_tf != nullptr;
+    if (post_tf) {
+        TRY(dev_alloc(e, e->post_tf, (size_t)n_post * sizeof(int32_t)));
+        if (n_post > 0) CK(cudaMemcpyAsync(e->post_tf.p, post_tf, (size_t)n_post * sizeof(int32_t), cudaMemcpyDefault, e->stream));
+    }
+    TRY(dev_alloc(e, e->idf, (size_t)n_terms * sizeof(double)));
+    if (n_terms > 0) CK(cudaMemcpyAsync(e->idf.p, idf, (size_t)n_terms * sizeof(double), cudaMemcpyDefault, e->stream));
+    TRY(dev_alloc(e, e->doc_len, (size_t)n_docs * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->kd, (size_t)n_docs * sizeof(double)));
+    if (n_docs > 0) {
+        CK(cudaMemcpyAsync(e->doc_len.p, doc_len, (size_t)n_docs * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+        // webui.py:145  k1 * (1 - b + b * (dl / bm25_avgdl)), same operation order, no contraction
+        kd_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, e->stream>>>(e->doc_len.as<int64_t>(), n_docs, avgdl, e->p.k1, e->p.b,
+                                                                          1.0 - e->p.b, e->kd.as<double>());
+        LAUNCHED(e);
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    e->avgdl = avgdl;
+    e->n_vocab = n_terms;
+    e->n_bm25 = n_docs;
+    e->n_post = n_post;
+    return AIS_OK;
+}
+
+// ---- seams ----------------------------------------------------------------------------------------
+int ais_dot_scores(ais_engine* e, const float* q, float* out) {
+    if (!e || !q || !out) return fail(AIS_ERR_INVALID, "NULL argument");
+    DeviceGuard g(e->device);
+    if (e->n_vec <= 0) return fail(AIS_ERR_NOT_LOADED, "no doc vectors loaded");
+    TRY(ensure_work(e));
+    memcpy(e->h_q, q, DIM * sizeof(float));
+    CK(cudaMemcpyAsync(e->d_q.p, e->h_q, DIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    init_keys_kernel<<<1, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(), e->maxr_key.as<uint64_t>(),
+                                             e->status.as<int32_t>(), 1, 1);
+    LAUNCHED(e);
+    TRY(launch_scan(e, e->d_q.as<float>(), 1, e->sim.as<float>(), e->maxs_key.as<uint32_t>()));
+    CK(cudaMemcpyAsync(out, e->sim.p, (size_t)e->n_vec * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return AIS_OK;
+}
+
+int ais_bm25_scores(ais_engine* e, const int32_t* term_ids, const double* weights, int32_t n_terms, double* out) {
+    if (!e || !out || (n_terms > 0 && (!term_ids || !weights))) return fail(AIS_ERR_INVALID, "NULL argument");
+    DeviceGuard g(e->device);
+    if (e->n_bm25 < 0) return fail(AIS_ERR_NOT_LOADED, "BM25 index not loaded");
+    TRY(ensure_work(e));
+    ais_query q{nullptr, term_ids, weights, n_terms};
+    TRY(upload_queries(e, &q, 1, false, true));
+    init_keys_kernel<<<1, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(), e->maxr_key.as<uint64_t>(),
+                                             e->status.as<int32_t>(), 1, 1);
+    LAUNCHED(e);
+    TRY(launch_bm25(e, 1));
+    CK(cudaMemcpyAsync(out, e->bm25.p, (size_t)e->n_bm25 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return AIS_OK;
+}
+
+int ais_final_scores(ais_engine* e, const ais_query* q, double* out) {
+    if (!e || !q || !out) return fail(AIS_ERR_INVALID, "NULL argument");
+    DeviceGuard g(e->device);
+    TRY(do_score(e, q, 1, e->maxes_own.as<double>()));
+    TRY(do_combine(e, 1, e->maxes_own.as<double>(), 1, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), false));
+    CK(cudaMemcpyAsync(out, e->fin.p, (size_t)e->n() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return AIS_OK;
+}
+
+// ---- the fused path -----------------------------------------------------------------------------------
+int ais_search(ais_engine* e, const ais_query* queries, int32_t n_queries, int32_t topn, int32_t prf_mode, ais_infer_cb cb,
+               void* cb_ctx, int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status) {
+    if (!e || (n_queries > 0 && !queries)) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (topn < 1) return fail(AIS_ERR_INVALID, "topn must be >= 1");
+    if (prf_mode < AIS_PRF_CALLBACK || prf_mode > AIS_PRF_OFF) return fail(AIS_ERR_INVALID, "unknown prf_mode %d", prf_mode);
+    DeviceGuard g(e->device);
+    TRY(check_loaded(e));
+    TRY(need_whole_index(e));
+    for (int q0 = 0; q0 < n_queries; q0 += e->p.max_batch) {
+        const int nq = n_queries - q0 < e->p.max_batch ? n_queries - q0 : e->p.max_batch;
+        TRY(run_batch(e, queries + q0, q0, nq, topn, prf_mode, cb, cb_ctx, out_ids ? out_ids + (size_t)q0 * topn : nullptr,
+                      out_scores ? out_scores + (size_t)q0 * topn : nullptr, out_counts ? out_counts + q0 : nullptr,
+                      out_status ? out_status + q0 : nullptr));
+    }
+    return AIS_OK;
+}
+
+int ais_rerank(ais_engine* e, const double* final_scores, int32_t topn, int32_t prf_mode, ais_infer_cb cb, void* cb_ctx,
+               int64_t* out_ids, double* out_scores, int32_t* out_count, int32_t* out_status) {
+    if (!e || !final_scores) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (topn < 1) return fail(AIS_ERR_INVALID, "topn must be >= 1");
+    DeviceGuard g(e->device);
+    TRY(check_loaded(e));
+    TRY(need_whole_index(e));
+    TRY(ensure_work(e));
+    CK(cudaMemcpyAsync(e->fin.p, final_scores, (size_t)e->n() * sizeof(double), cudaMemcpyDefault, e->stream));
+    CK(cudaMemsetAsync(e->status.p, 0, sizeof(int32_t), e->stream));
+    e->cur_nq = 1;
+    return run_batch(e, nullptr, 0, 1, topn, prf_mode, cb, cb_ctx, out_ids, out_scores, out_count, out_status);
+}
+
+// filter_searched_result(sorted_scores) webui.py:63-80 on a caller-supplied, already sorted list
+int ais_filter_sorted(ais_engine* e, const int64_t* ids, const double* scores, int64_t n, int64_t* out_ids, double* out_scores,
+                      int64_t* out_count) {
+    if (!e || !out_count || (n > 0 && (!ids || !scores || !out_ids || !out_scores))) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (n < 0 || n >= (1LL << 31)) return fail(AIS_ERR_INVALID, "list length outside [0, 2^31)");
+    *out_count = 0;
+    if (n == 0) return AIS_OK;
+    DeviceGuard g(e->device);
+    Buf d_sc, d_oi, d_os;
+    int st = AIS_OK;
+    auto body = [&]() -> int {
+        TRY(dev_alloc(e, e->fs_keys, (size_t)n * sizeof(uint64_t)));
+        TRY(dev_alloc(e, e->fs_ids, (size_t)n * sizeof(int64_t)));
+        TRY(dev_alloc(e, e->fs_count, sizeof(int64_t) * 2));
+        TRY(dev_alloc(e, d_sc, (size_t)n * sizeof(double)));
+        TRY(dev_alloc(e, d_oi, (size_t)n * sizeof(int64_t)));
+        TRY(dev_alloc(e, d_os, (size_t)n * sizeof(double)));
+        TRY(dev_alloc(e, e->out_count, sizeof(int32_t)));
+        TRY(dev_alloc(e, e->out_amb, sizeof(int32_t)));
+        CK(cudaMemcpyAsync(d_sc.p, scores, (size_t)n * sizeof(double), cudaMemcpyDefault, e->stream));
+        CK(cudaMemcpyAsync(e->fs_ids.p, ids, (size_t)n * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+        CK(cudaMemcpyAsync(e->fs_count.p, &n, sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+        keys_from_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d_sc.as<double>(), n, e->fs_keys.as<uint64_t>());
+        LAUNCHED(e);
+        TailParams tp;
+        tp.thresh = e->p.diff_filter_thresh;
+        tp.topn = (int)n;
+        tp.depth = 0;
+        tp.normalize = 0;
+        tp.n_total = n;
+        tail_kernel<<<1, SEL_THREADS, 0, e->stream>>>(e->fs_keys.as<uint64_t>(), e->fs_ids.as<int64_t>(), 0, nullptr,
+                                                     e->fs_count.as<int64_t>(), nullptr, nullptr, tp, d_oi.as<int64_t>(),
+                                                     d_os.as<double>(), e->out_count.as<int32_t>(), e->out_amb.as<int32_t>());
+        LAUNCHED(e);
+        int32_t cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, e->out_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (cnt > 0) {
+            CK(cudaMemcpyAsync(out_ids, d_oi.p, (size_t)cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaMemcpyAsync(out_scores, d_os.p, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+        }
+        *out_count = cnt;
+        return AIS_OK;
+    };
+    st = body();
+    dev_free(e, d_sc);
+    dev_free(e, d_oi);
+    dev_free(e, d_os);
+    return st;
+}
+
+// ---- staged form ----------------------------------------------------------------------------------------
+int ais_stage_score(ais_engine* e, const ais_query* queries, int32_t nq, double* d_maxes) {
+    if (!e || !queries || !d_maxes) return fail(AIS_ERR_INVALID, "NULL argument");
+    DeviceGuard g(e->device);
+    return do_score(e, queries, nq, d_maxes);
+}
+int ais_stage_combine(ais_engine* e, int32_t nq, const double* d_maxes, int32_t k, uint64_t* d_cand_keys, int64_t* d_cand_ids) {
+    if (!e || !d_maxes || !d_cand_keys || !d_cand_ids) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (nq != e->cur_nq) return fail(AIS_ERR_INVALID, "nq %d differs from the scored batch (%d)", nq, e->cur_nq);
+    DeviceGuard g(e->device);
+    return do_combine(e, nq, d_maxes, k, d_cand_keys, d_cand_ids, false);
+}
+int ais_stage_top(ais_engine* e, int32_t nq, int32_t n_lists, int32_t k, const uint64_t* d_cand_keys, const int64_t* d_cand_ids,
+                  int64_t* out_top_ids, double* out_top_scores, float* d_rows) {
+    if (!e || !d_cand_keys || !d_cand_ids || n_lists < 1) return fail(AIS_ERR_INVALID, "bad argument");
+    if (nq != e->cur_nq) return fail(AIS_ERR_INVALID, "nq %d differs from the scored batch (%d)", nq, e->cur_nq);
+    DeviceGuard g(e->device);
+    return do_top(e, nq, n_lists, k, d_cand_keys, d_cand_ids, out_top_ids, out_top_scores, d_rows);
+}
+int ais_stage_set_status(ais_engine* e, int32_t nq, const int32_t* status) {
+    if (!e || !status || nq != e->cur_nq) return fail(AIS_ERR_INVALID, "bad argument");
+    DeviceGuard g(e->device);
+    CK(cudaMemcpyAsync(e->status.p, status, (size_t)nq * sizeof(int32_t), cudaMemcpyDefault, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return AIS_OK;
+}
+int ais_stage_requery(ais_engine* e, int32_t nq, const float* q2, const float* d_rows, int32_t prf_mode, int32_t k,
+                      double* d_max_r, uint64_t* d_cand_keys, int64_t* d_cand_ids) {
+    if (!e || !d_max_r || !d_cand_keys || !d_cand_ids) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (nq != e->cur_nq) return fail(AIS_ERR_INVALID, "nq %d differs from the scored batch (%d)", nq, e->cur_nq);
+    DeviceGuard g(e->device);
+    return do_requery(e, nq, q2, d_rows, prf_mode, k, d_max_r, d_cand_keys, d_cand_ids);
+}
+int ais_stage_requery_select(ais_engine* e, int32_t nq, int32_t k, uint64_t* d_cand_keys, int64_t* d_cand_ids) {
+    if (!e || !d_cand_keys || !d_cand_ids) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (nq != e->cur_nq || !e->cur_prf) return fail(AIS_ERR_INVALID, "no second pass to re-select from");
+    DeviceGuard g(e->device);
+    return do_requery_select(e, nq, k, d_cand_keys, d_cand_ids);
+}
+int ais_stage_finish(ais_engine* e, int32_t nq, int32_t n_lists, int32_t k, const uint64_t* d_cand_keys, const int64_t* d_cand_ids,
+                     const double* d_max_r, int32_t topn, int64_t* out_ids, double* out_scores, int32_t* out_counts,
+                     int32_t* out_status, int32_t* out_ambiguous) {
+    if (!e || !d_cand_keys || !d_cand_ids || n_lists < 1) return fail(AIS_ERR_INVALID, "bad argument");
+    if (nq != e->cur_nq) return fail(AIS_ERR_INVALID, "nq %d differs from the scored batch (%d)", nq, e->cur_nq);
+    DeviceGuard g(e->device);
+    return do_finish(e, nq, n_lists, k, d_cand_keys, d_cand_ids, d_max_r, topn, out_ids, out_scores, out_counts, out_status,
+                     out_ambiguous);
+}
+int ais_stage_export_keys(ais_engine* e, int32_t query, int32_t second_pass, uint64_t* d_keys, int64_t* d_ids) {
+    if (!e || !d_keys || !d_ids || query < 0 || query >= e->cur_nq) return fail(AIS_ERR_INVALID, "bad argument");
+    DeviceGuard g(e->device);
+    return do_export_keys(e, query, second_pass, d_keys, d_ids);
+}
+int ais_stage_sort_finish(ais_engine* e, int32_t query, uint64_t* d_keys, int64_t* d_ids, int64_t n_entries, const double* d_max_r,
+                          int32_t topn, int64_t* out_ids, double* out_scores, int32_t* out_count, int32_t* out_status) {
+    if (!e || !d_keys || !d_ids || query < 0 || query >= e->cur_nq || n_entries < 0 || topn < 1)
+        return fail(AIS_ERR_INVALID, "bad argument");
+    DeviceGuard g(e->device);
+    return do_sort_finish(e, query, d_keys, d_ids, n_entries, d_max_r, topn, out_ids, out_scores, out_count, out_status);
+}
+
+// ---- introspection ----------------------------------------------------------------------------------------
+int ais_set_profiling(ais_engine* e, int on) {
+    if (!e) return fail(AIS_ERR_INVALID, "NULL engine");
+    e->profiling = on != 0;
+    return AIS_OK;
+}
+static int drain_events(ais_engine* e) {
+    if (e->ev_pending.empty()) return AIS_OK;
+    CK(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i + 1 < e->ev_pending.size(); i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e->ev_pending[i], e->ev_pending[i + 1]));
+        e->scan_ms_total += ms;
+        e->ev_free.push_back(e->ev_pending[i]);
+        e->ev_free.push_back(e->ev_pending[i + 1]);
+    }
+    e->ev_pending.clear();
+    return AIS_OK;
+}
+int ais_get_stats(ais_engine* e, ais_stats* out) {
+    if (!e || !out) return fail(AIS_ERR_INVALID, "NULL argument");
+    DeviceGuard g(e->device);
+    TRY(drain_events(e));
+    out->n_docs = e->n_vec;
+    out->n_postings = e->n_post;
+    out->dim = DIM;
+    out->n_terms = e->n_vocab;
+    out->scan_launches = e->scan_launches;
+    out->scan_ms_total = e->scan_ms_total;
+    out->kernel_launches = e->kernel_launches;
+    out->fullsort_fallbacks = e->fullsort_fallbacks;
+    out->bytes_device = e->bytes_device;
+    return AIS_OK;
+}
+int ais_reset_stats(ais_engine* e) {
+    if (!e) return fail(AIS_ERR_INVALID, "NULL engine");
+    DeviceGuard g(e->device);
+    TRY(drain_events(e));
+    e->scan_launches = e->kernel_launches = e->fullsort_fallbacks = 0;
+    e->scan_ms_total = 0.0;
+    return AIS_OK;
+}
+int ais_synchronize(ais_engine* e) {
+    if (!e) return fail(AIS_ERR_INVALID, "NULL engine");
+    DeviceGuard g(e->device);
+    CK(cudaStreamSynchronize(e->stream));
+    return AIS_OK;
+}
+
+}  // extern "C"

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1)
 scan_kernel(const float* __restrict__ rows, int64_t n, const float* __restrict__ queries,  // [QT][DIM]
             float* __restrict__ out, int64_t ld,                                             // [QT][ld]
             uint32_t* __restrict__ max_keys,                                                 // [QT] fkey images
-            int evict_first) {
+            int nq_live, int evict_first) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* stage_base = smem_raw;
     float* qs = reinterpret_cast<float*>(smem_raw + (size_t)SCAN_STAGES * TILE_BYTES);
@@ -112,7 +112,7 @@ scan_kernel(const float* __restrict__ rows, int64_t n, const float* __restrict__
 #pragma unroll
         for (int qi = 0; qi < QT; ++qi) {
             const float v = (acc[qi].x + acc[qi].y) + (acc[qi].z + acc[qi].w);
-            if (live) {
+            if (live && qi < nq_live) {
                 out[(int64_t)qi * ld + row] = v;
                 lmax[qi] = fmaxf(lmax[qi], v);
             }
@@ -123,7 +123,7 @@ scan_kernel(const float* __restrict__ rows, int64_t n, const float* __restrict__
 #pragma unroll
     for (int qi = 0; qi < QT; ++qi) {
         const float m = warp_max(lmax[qi]);
-        if (lane == 0) atomicMax(&max_keys[qi], fkey(m));
+        if (lane == 0 && qi < nq_live) atomicMax(&max_keys[qi], fkey(m));
     }
 }
 

@@ -267,30 +267,35 @@ struct CandF {
     const uint64_t* keys;
     const int64_t* ids;
     int64_t list_stride, q_stride;
-    int qi, k;
+    int qi, k, list0;
     __device__ __forceinline__ bool operator()(int64_t i, uint64_t& key, int64_t& id) const {
         const int64_t list = i / k, pos = i - list * k;
-        const size_t o = (size_t)(list * list_stride + (int64_t)qi * q_stride + pos);
+        const size_t o = (size_t)((list + list0) * list_stride + (int64_t)qi * q_stride + pos);
         key = keys[o];
         id = ids[o];
         return key != KEY_EMPTY;
     }
 };
-// one block per query; writes the sorted top-k_out (keys + ids) and its count
+// grid (n_groups, nq): block (g, q) merges lists [g*group, min(n_lists, (g+1)*group)) of query q into
+// the sorted top-k_out written at out[(q*n_groups + g)*out_stride ...] (+ its count).  A two-level
+// tree (group = 16, then one block per query) keeps the serial part short.
 __global__ void __launch_bounds__(SEL_THREADS)
-merge_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ ids, int n_lists, int64_t list_stride,
-             int64_t q_stride, int k_in, int k_out,
+merge_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ ids, int n_lists, int group,
+             int64_t list_stride, int64_t q_stride, int k_in, int k_out,
              uint64_t* __restrict__ out_keys, int64_t* __restrict__ out_ids, int64_t out_stride,
              int32_t* __restrict__ out_count) {
     __shared__ SelBuf sb;
-    const int qi = blockIdx.x;
+    const int g = blockIdx.x, qi = blockIdx.y;
+    const int list0 = g * group;
+    const int my_lists = (n_lists - list0 < group) ? (n_lists - list0) : group;
     sel_init(sb);
-    CandF f{keys, ids, list_stride, q_stride, qi, k_in};
-    const int64_t total = (int64_t)n_lists * k_in;
+    CandF f{keys, ids, list_stride, q_stride, qi, k_in, list0};
+    const int64_t total = (int64_t)my_lists * k_in;
     if (total > 0) sel_stream(sb, 0, total, k_out, f);
     else { __syncthreads(); sel_prune(sb, k_out); }
-    sel_write(sb, k_out, out_keys + (size_t)qi * out_stride, out_ids + (size_t)qi * out_stride);
-    if (threadIdx.x == 0) out_count[qi] = sb.count;
+    const size_t o = ((size_t)qi * gridDim.x + g) * (size_t)out_stride;
+    sel_write(sb, k_out, out_keys + o, out_ids + o);
+    if (threadIdx.x == 0 && out_count) out_count[qi * gridDim.x + g] = sb.count;
 }
 
 // ---- PRF: stored rows of the top docs, centroid, re-query vector (webui.py:195-205) ----------

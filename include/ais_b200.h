@@ -122,6 +122,11 @@ int ais_set_shard(ais_engine* e, int64_t first_doc_id, int64_t n_total_docs);
  * genmodel.py:168-175; rows are stored RAW, never normalised).  host-or-device pointer.
  * Appendable shard by shard. */
 int ais_load_vectors(ais_engine* e, const float* rows, int64_t n, int32_t dim, int64_t first_row);
+/* Pre-size the row store (avoids re-allocation while gensim shards are appended one by one). */
+int ais_reserve_docs(ais_engine* e, int64_t n_docs);
+/* Declare n_docs rows resident and hand out the device pointer of the row store [n_docs x 300] so a
+ * caller that already has the rows on the device (or generates them there) can write them in place. */
+int ais_vectors_device_ptr(ais_engine* e, int64_t n_docs, float** out_rows);
 /* The BM25 index of genmodel.py:51-99 (bm25_corpus / bm25_idf / bm25_doc_lengths / bm25_avgdl) as
  * tag-major posting lists with LOCAL doc ids ascending inside each list.  post_tf may be NULL
  * (every tf == 1).  idf[t] = 0 for terms absent from bm25_idf (webui.py:140).  host-or-device. */
@@ -151,6 +156,11 @@ int ais_search(ais_engine* e, const ais_query* queries, int32_t n_queries, int32
 int ais_rerank(ais_engine* e, const double* final_scores, int32_t topn, int32_t prf_mode, ais_infer_cb cb,
                void* cb_ctx, int64_t* out_ids, double* out_scores, int32_t* out_count, int32_t* out_status);
 
+/* filter_searched_result(sorted_scores) webui.py:63-80 on a caller-supplied list of n (doc id, score)
+ * pairs sorted best first (host-or-device arrays).  Writes *out_count <= n pairs (host arrays [n]). */
+int ais_filter_sorted(ais_engine* e, const int64_t* ids, const double* scores, int64_t n, int64_t* out_ids,
+                      double* out_scores, int64_t* out_count);
+
 /* --- staged form of ais_search for doc-sharded multi-GPU search ------------------------- */
 /* All d_* arguments are DEVICE pointers owned by the caller (e.g. torch tensors) so that the
  * caller can run its collectives (NCCL all-reduce MAX / all-gather) on them between stages, on
@@ -173,18 +183,32 @@ int ais_stage_top(ais_engine* e, int32_t nq, int32_t n_lists, int32_t k, const u
  * the 0.7/0.3 blend, this shard's max and its top-k candidates (top docs excluded). */
 int ais_stage_requery(ais_engine* e, int32_t nq, const float* q2, const float* d_rows, int32_t prf_mode,
                       int32_t k, double* d_max_r /*[nq]*/, uint64_t* d_cand_keys, int64_t* d_cand_ids);
+/* host-side PRF (callback mode in a sharded caller): per-query status decided on the host
+ * (AIS_Q_NAN_WEIGHTS ...) before ais_stage_requery; such queries return count 0. */
+int ais_stage_set_status(ais_engine* e, int32_t nq, const int32_t* status);
 /* merge the all-gathered second-pass candidates, normalise by the (all-reduced) max, apply
- * filter_searched_result and write the results (host arrays).  A query whose filter outcome
- * depends on scores beyond the k candidates gets out_ambiguous[q] = 1 (caller repeats
- * ais_stage_requery_select with a larger k; k = 0 there means "whole shard"). */
+ * filter_searched_result and write the results (host arrays).  d_max_r == NULL selects the
+ * no-PRF branch (webui.py:247-253): the candidates are the sorted combined scores of
+ * ais_stage_combine and no docs are pinned.  A query whose filter outcome depends on scores
+ * beyond the k candidates gets out_ambiguous[q] = 1: the caller repeats ais_stage_requery_select
+ * (or ais_stage_combine) with k = ais_max_select_k(), and if still ambiguous sorts everything
+ * with ais_stage_export_keys + ais_stage_sort_finish. */
 int ais_stage_finish(ais_engine* e, int32_t nq, int32_t n_lists, int32_t k, const uint64_t* d_cand_keys,
                      const int64_t* d_cand_ids, const double* d_max_r, int32_t topn, int64_t* out_ids,
                      double* out_scores, int32_t* out_counts, int32_t* out_status, int32_t* out_ambiguous);
-/* re-select second-pass candidates with another k without re-scanning (k <= ais_max_select_k(),
- * or k == 0: every doc of the shard, sorted, written to the engine's full-sort buffers whose
- * device pointers and length are returned). */
+/* re-select second-pass candidates with another k without re-scanning (k <= ais_max_select_k()). */
 int ais_stage_requery_select(ais_engine* e, int32_t nq, int32_t k, uint64_t* d_cand_keys, int64_t* d_cand_ids);
 int ais_max_select_k(void);
+/* Exact fallback for an ambiguous filter outcome: every shard exports the keys of ALL its docs for
+ * one query (second_pass = 1: the blended R with the pinned top docs blanked; 0: the combined scores)
+ * into caller arrays [n_local]; the caller concatenates the shards' exports (all-gather) into device
+ * arrays of ais_sort_capacity(n_entries) slots and one engine sorts them and applies the exact
+ * filter_searched_result. */
+int ais_stage_export_keys(ais_engine* e, int32_t query, int32_t second_pass, uint64_t* d_keys, int64_t* d_ids);
+int64_t ais_sort_capacity(int64_t n_entries);
+int ais_stage_sort_finish(ais_engine* e, int32_t query, uint64_t* d_keys, int64_t* d_ids, int64_t n_entries,
+                          const double* d_max_r /* NULL: no-PRF branch */, int32_t topn, int64_t* out_ids,
+                          double* out_scores, int32_t* out_count, int32_t* out_status);
 
 /* --- introspection ----------------------------------------------------------------------- */
 int ais_set_profiling(ais_engine* e, int on);   /* CUDA-event timing of every scan launch */

@@ -11,6 +11,10 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: takes more than a few seconds")
+    # the C-ABI library must exist before anything imports ais_b200.binding (nvcc cross-compiles without a GPU;
+    # on the GPU box the prebuilt .so travels with the snapshot and this is a no-op)
+    import __graft_entry__
+    __graft_entry__.build()
 
 
 def pytest_collection_modifyitems(config, items):

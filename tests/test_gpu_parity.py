@@ -1,0 +1,150 @@
+"""-m gpu: the CUDA path, called through the C ABI / the webui.py-compatible module, against
+(a) the golden fixtures recorded from the reference itself and (b) the oracle port on fresh indexes."""
+import numpy as np
+import pytest
+
+from golden_util import load_filter_cases, load_index, load_results, load_seams
+from gpu_util import SCORE_RTOL, assert_same, capture, install
+import ais_b200  # noqa: F401
+from ais_b200 import engine as E, query as Q, synth, webui_api
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def main_index():
+    return load_index("main")
+
+
+@pytest.mark.parametrize("prf_mode", ["callback", "stored_rows"])
+def test_golden_results_main(main_index, prf_mode):
+    """Every recorded find_similar_documents outcome of the reference: ids, order, scores, exceptions."""
+    install(main_index, prf_mode=prf_mode)
+    for rec in load_results("main")["results"]:
+        got = capture(webui_api.find_similar_documents, rec["query"], rec["topn"])
+        want = ("err", rec["error"], rec["message"]) if "error" in rec else ("ok", rec["ids"], rec["scores"])
+        assert_same(got, want, rec["query"])
+
+
+def test_golden_results_tiny_no_prf_branch():
+    """N <= 10: webui.py:247-253."""
+    install(load_index("tiny"))
+    for rec in load_results("tiny")["results"]:
+        got = capture(webui_api.find_similar_documents, rec["query"], rec["topn"])
+        assert_same(got, ("ok", rec["ids"], rec["scores"]), rec["query"])
+
+
+def test_golden_seams(main_index):
+    """index[vec], compute_bm25_scores and the combined scores against the reference's own vectors."""
+    eng = install(main_index)
+    z = load_seams()
+    for k in range(4):
+        text = str(z["q%d_text" % k])
+        vec = webui_api.normalize_and_apply_weight_doc2vec(text)
+        sims = webui_api.index[vec]
+        ref = z["q%d_sims" % k]
+        assert sims.dtype == np.float32 and sims.shape == ref.shape
+        assert np.abs(sims - ref).max() <= 1e-5 * np.abs(ref).max()
+        wts = dict(zip(z["q%d_terms" % k].tolist(), z["q%d_weights" % k].tolist()))
+        bm25 = webui_api.compute_bm25_scores(query_weights=wts)
+        assert bm25.dtype == np.float64
+        assert np.array_equal(bm25, z["q%d_bm25" % k])                    # bit-exact, -inf masks included
+        q = Q.make_query(text, main_index.token2id, webui_api.model.infer_vector)
+        fin = eng.final_scores(q)
+        rf = z["q%d_final" % k]
+        assert np.array_equal(np.isneginf(fin), np.isneginf(rf))          # masks bit-exact
+        live = ~np.isneginf(rf)
+        assert np.abs(fin[live] - rf[live]).max() <= 1e-5 * np.abs(rf[live]).max()
+    names = z["terms_form_tags"].tolist()
+    assert np.array_equal(webui_api.compute_bm25_scores(query_terms=names), z["terms_form_bm25"])
+
+
+def test_filter_known_answers(main_index):
+    install(main_index)
+    for c in load_filter_cases():
+        res = webui_api.filter_searched_result(c["input"])
+        assert [d for d, _ in res] == c["ids"]
+        assert [float(s) for _, s in res] == c["scores"]
+
+
+def test_rerank_seam_matches_oracle(main_index):
+    install(main_index)
+    P = port.OraclePort(main_index)
+    z = load_seams()
+    for k in range(4):
+        fin = z["q%d_final" % k]
+        for topn in (5, 100, 800):
+            got = capture(webui_api.get_doc2vec_based_reranked_scores, fin, topn)
+            want = capture(P.rerank, fin, topn)
+            assert_same(got, want, "rerank q%d topn %d" % (k, topn))
+
+
+@pytest.mark.parametrize("n_docs,vocab,tf_frac", [(50000, 3000, 0.0), (7000, 400, 0.03), (33, 20, 0.0), (11, 12, 0.0)])
+def test_fresh_index_vs_oracle(n_docs, vocab, tf_frac):
+    idx = synth.generate_index(n_docs, vocab_size=vocab, seed=1234 + n_docs, tf_gt1_fraction=tf_frac)
+    P = port.OraclePort(idx)
+    queries = synth.generate_queries(idx, 24, seed=n_docs)
+    for prf_mode in ("callback", "stored_rows"):
+        install(idx, prf_mode=prf_mode)
+        for q in queries:
+            for topn in ((100, 800) if n_docs > 1000 else (100,)):
+                assert_same(capture(webui_api.find_similar_documents, q, topn), capture(P.find_similar_documents, q, topn), q)
+
+
+def test_batched_queries_equal_single_queries():
+    idx = synth.generate_index(40000, vocab_size=2000, seed=77)
+    queries = synth.generate_queries(idx, 37, seed=3)
+    t2i = idx.token2id
+    infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
+    qs = [Q.make_query(q, t2i, infer) for q in queries]
+    single = E.SearchEngine.from_index(idx, max_batch=1)
+    ref = single.search_raw(qs, 100, E.PRF_STORED_ROWS)
+    for mb in (2, 3, 8, 16):
+        eng = E.SearchEngine.from_index(idx, max_batch=mb)
+        got = eng.search_raw(qs, 100, E.PRF_STORED_ROWS)
+        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+        for q in range(len(qs)):
+            c = ref[2][q]
+            assert np.array_equal(got[0][q, :c], ref[0][q, :c]), (mb, q)
+            assert np.array_equal(got[1][q, :c], ref[1][q, :c]), (mb, q)      # same kernels, same order: bit-equal
+        eng.close()
+
+
+def test_constants_are_honoured_at_call_time():
+    idx = synth.generate_index(6000, vocab_size=500, seed=5)
+    P = port.OraclePort(idx)
+    install(idx)
+    q = synth.generate_queries(idx, 3, seed=9)
+    try:
+        webui_api.BM25_WEIGHT, webui_api.DOC2VEC_WEIGHT = 0.3, 0.7
+        webui_api.ORIGINAL_SCORE_WEIGHT, webui_api.RERANKED_SCORE_WEIGHT = 0.6, 0.4
+        webui_api.DIFF_FILTER_THRESH = 1e-4              # near-ties now common: exercises the exact filter fallback
+        P.consts.update(BM25_WEIGHT=0.3, DOC2VEC_WEIGHT=0.7, ORIGINAL_SCORE_WEIGHT=0.6, RERANKED_SCORE_WEIGHT=0.4,
+                        DIFF_FILTER_THRESH=1e-4)
+        for text in q:
+            for topn in (20, 100, 800):
+                assert_same(capture(webui_api.find_similar_documents, text, topn),
+                            capture(P.find_similar_documents, text, topn), text)
+    finally:
+        webui_api.BM25_WEIGHT = webui_api.DOC2VEC_WEIGHT = 0.5
+        webui_api.ORIGINAL_SCORE_WEIGHT, webui_api.RERANKED_SCORE_WEIGHT = 0.7, 0.3
+        webui_api.DIFF_FILTER_THRESH = 1e-6
+
+
+def test_filter_fallback_is_exact_and_counted():
+    """One near-tie inside the prefix and none (or one) elsewhere: the outcome depends on the whole list."""
+    idx = synth.generate_index(3000, vocab_size=300, seed=21)
+    P = port.OraclePort(idx)
+    eng = install(idx)
+    P.consts["DIFF_FILTER_THRESH"] = 3e-5
+    webui_api.DIFF_FILTER_THRESH = 3e-5
+    try:
+        eng.reset_stats()
+        for text in synth.generate_queries(idx, 30, seed=2):
+            for topn in (12, 40):
+                assert_same(capture(webui_api.find_similar_documents, text, topn),
+                            capture(P.find_similar_documents, text, topn), text)
+        assert eng.stats()["fullsort_fallbacks"] > 0
+    finally:
+        webui_api.DIFF_FILTER_THRESH = 1e-6
