@@ -280,7 +280,7 @@ int launch_scan_t(ais_engine* e, const float* d_q, int nq, float* out, uint32_t*
         }
         CK(cudaEventRecord(a, e->stream));
     }
-    scan_kernel<QT><<<grid, SCAN_THREADS, scan_smem_bytes<QT>(), e->stream>>>(
+    scan_kernel<QT><<<grid, ScanCfg<QT>::THREADS, scan_smem_bytes<QT>(), e->stream>>>(
         e->rows.as<float>(), e->n_vec, d_q, out, e->ld, max_keys, nq, 1);
     LAUNCHED(e);
     e->scan_launches++;
@@ -617,6 +617,8 @@ double np_sum_host(const double* a, int n) {
 int run_batch(ais_engine* e, const ais_query* qs, int q_index0, int nq, int topn, int prf_mode, ais_infer_cb cb, void* ctx,
               int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status) {
     const int depth = e->p.prf_depth;
+    TRY(check_loaded(e));
+    TRY(ensure_work(e));            // every buffer exists BEFORE its pointer is taken
     double* maxes = e->maxes_own.as<double>();
     if (qs) TRY(do_score(e, qs, nq, maxes));
     const bool prf = prf_mode != AIS_PRF_OFF && e->total() > depth;     // webui.py:193 `len(sims) > 10`
@@ -931,6 +933,9 @@ int ais_bm25_scores(ais_engine* e, const int32_t* term_ids, const double* weight
 int ais_final_scores(ais_engine* e, const ais_query* q, double* out) {
     if (!e || !q || !out) return fail(AIS_ERR_INVALID, "NULL argument");
     DeviceGuard g(e->device);
+    TRY(check_loaded(e));
+    TRY(ensure_work(e));
+    TRY(ensure_sel(e, 1));
     TRY(do_score(e, q, 1, e->maxes_own.as<double>()));
     TRY(do_combine(e, 1, e->maxes_own.as<double>(), 1, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), false));
     CK(cudaMemcpyAsync(out, e->fin.p, (size_t)e->n() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));

@@ -122,7 +122,10 @@ class SearchEngine:
     def use_torch_stream(self) -> None:
         """Run on torch's current CUDA stream so torch events / NCCL collectives order with the kernels."""
         import torch
-        check(lib.ais_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        # handle 0 is torch's (legacy) default stream; the C ABI reserves NULL for "the engine's own stream",
+        # so name the default stream by its explicit handle cudaStreamLegacy (0x1)
+        check(lib.ais_set_stream(self._h, C.c_void_p(s if s else 1)))
 
     # ---- index staging (load_model, webui.py:649-689) ------------------------------------------
     def load_vectors(self, rows, first_row: int = 0) -> None:

@@ -112,7 +112,8 @@ void ais_default_params(ais_params* p);
 int ais_create(ais_engine** out, int device_id, const ais_params* p /* NULL = defaults */);
 int ais_destroy(ais_engine* e);
 int ais_set_params(ais_engine* e, const ais_params* p);
-/* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL = the engine's own stream. */
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL = the engine's own (non-blocking)
+ * stream.  To run on the legacy default stream pass its explicit handle cudaStreamLegacy (0x1). */
 int ais_set_stream(ais_engine* e, void* cuda_stream);
 /* This engine holds docs [first_doc_id, first_doc_id + n_local) of an index of n_total docs. */
 int ais_set_shard(ais_engine* e, int64_t first_doc_id, int64_t n_total_docs);

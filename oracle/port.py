@@ -210,7 +210,8 @@ class OraclePort:
         return [(round(docid), val) for docid, val in mean.tolist()]
 
     # ---- webui.py:189-253 ---------------------------------------------------
-    def rerank(self, final_scores: np.ndarray, topn: int) -> List[Tuple[int, float]]:
+    def rerank_sorted(self, final_scores: np.ndarray) -> List[Tuple[int, float]]:
+        """The sorted (doc id, score) list of webui.py:189-237 right BEFORE filter_searched_result."""
         n = len(final_scores)
         if self.faithful:
             sims = sorted(list(enumerate(final_scores)), key=lambda it: -it[1])
@@ -238,12 +239,21 @@ class OraclePort:
                 ro = np.argsort(-R, kind="stable")
                 ro = ro[~np.isin(ro, np.asarray(top_ids))]
                 rest = list(zip(ro.tolist(), R[ro]))
-            out = filter_searched_result(head + rest, self.consts["DIFF_FILTER_THRESH"])
-            return out[: min(topn, len(out))]
+            return head + rest
         if not self.faithful:
             sims = list(zip(order.tolist(), final_scores[order]))
-        out = filter_searched_result(sims, self.consts["DIFF_FILTER_THRESH"])
+        return sims
+
+    def rerank(self, final_scores: np.ndarray, topn: int) -> List[Tuple[int, float]]:
+        out = filter_searched_result(self.rerank_sorted(final_scores), self.consts["DIFF_FILTER_THRESH"])
         return out[: min(topn, len(out))]
+
+    def find_sorted(self, new_doc: str) -> List[Tuple[int, float]]:
+        """find_similar_documents up to (not including) the filter: for tolerance analysis in tests."""
+        vec = self.query_vector(new_doc)
+        sims = self.index[vec]
+        weights, _, _ = parse_query_weights(new_doc, self.token2id, self.consts["REQUIRE_TAG_MAGIC_NUMBER"])
+        return self.rerank_sorted(self.combine(sims, self.bm25_scores(weights)))
 
     # ---- webui.py:345-390 ---------------------------------------------------
     def find_similar_documents(self, new_doc: str, topn: int = 50) -> List[Tuple[int, float]]:

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from golden_util import load_filter_cases, load_index, load_results, load_seams
-from gpu_util import SCORE_RTOL, assert_same, capture, install
+from gpu_util import SCORE_RTOL, assert_same, assert_same_or_filter_unstable, capture, install
 import ais_b200  # noqa: F401
 from ais_b200 import engine as E, query as Q, synth, webui_api
 from oracle import port
@@ -89,7 +89,9 @@ def test_fresh_index_vs_oracle(n_docs, vocab, tf_frac):
         install(idx, prf_mode=prf_mode)
         for q in queries:
             for topn in ((100, 800) if n_docs > 1000 else (100,)):
-                assert_same(capture(webui_api.find_similar_documents, q, topn), capture(P.find_similar_documents, q, topn), q)
+                assert_same_or_filter_unstable(capture(webui_api.find_similar_documents, q, topn),
+                                               capture(P.find_similar_documents, q, topn),
+                                               lambda: P.find_sorted(q), 1e-6, topn, q)
 
 
 def test_batched_queries_equal_single_queries():
@@ -124,8 +126,9 @@ def test_constants_are_honoured_at_call_time():
                         DIFF_FILTER_THRESH=1e-4)
         for text in q:
             for topn in (20, 100, 800):
-                assert_same(capture(webui_api.find_similar_documents, text, topn),
-                            capture(P.find_similar_documents, text, topn), text)
+                assert_same_or_filter_unstable(capture(webui_api.find_similar_documents, text, topn),
+                                               capture(P.find_similar_documents, text, topn),
+                                               lambda: P.find_sorted(text), 1e-4, topn, text)
     finally:
         webui_api.BM25_WEIGHT = webui_api.DOC2VEC_WEIGHT = 0.5
         webui_api.ORIGINAL_SCORE_WEIGHT, webui_api.RERANKED_SCORE_WEIGHT = 0.7, 0.3
@@ -133,18 +136,40 @@ def test_constants_are_honoured_at_call_time():
 
 
 def test_filter_fallback_is_exact_and_counted():
-    """One near-tie inside the prefix and none (or one) elsewhere: the outcome depends on the whole list."""
-    idx = synth.generate_index(3000, vocab_size=300, seed=21)
-    P = port.OraclePort(idx)
-    eng = install(idx)
-    P.consts["DIFF_FILTER_THRESH"] = 3e-5
-    webui_api.DIFF_FILTER_THRESH = 3e-5
-    try:
+    """with exactly one near-tie inside the first k entries the outcome depends on whether
+    ANY other near-tie exists in the whole list - the engine must sort everything to decide."""
+    n = 5000
+    idx = synth.generate_index(n, vocab_size=300, seed=21)
+    rng = np.random.default_rng(0)
+    base = 1.0 - np.arange(n) * 1e-4                 # every gap 1e-4 ...
+    base[17:] += 1e-4 - 3e-7                         # ... except ONE near-tie between ranks 16 and 17
+    final = np.empty(n)
+    perm = rng.permutation(n)
+    final[perm] = base
+    for tweak in ("one", "two_far", "none"):
+        f = final.copy()
+        if tweak == "two_far":
+            f[perm[4000:]] += 1e-4 - 2e-7            # a second near-tie far beyond any top-k prefix
+        if tweak == "none":
+            f[perm[17:]] -= 1e-4 - 3e-7              # no near-tie at all
+        # PRF off: sorted(final) -> filter -> [:topn]  (the webui.py:247-253 branch semantics)
+        eng = install(idx, prf_mode="off")
         eng.reset_stats()
-        for text in synth.generate_queries(idx, 30, seed=2):
-            for topn in (12, 40):
-                assert_same(capture(webui_api.find_similar_documents, text, topn),
-                            capture(P.find_similar_documents, text, topn), text)
-        assert eng.stats()["fullsort_fallbacks"] > 0
-    finally:
-        webui_api.DIFF_FILTER_THRESH = 1e-6
+        order = np.argsort(-f, kind="stable")
+        want = port.filter_searched_result(list(zip(order.tolist(), f[order])))[:20]
+        got = webui_api.get_doc2vec_based_reranked_scores(f, 20)
+        assert [d for d, _ in got] == [d for d, _ in want], tweak
+        assert [s for _, s in got] == [s for _, s in want], tweak
+        assert len(got) == {"one": 16, "two_far": 20, "none": 20}[tweak]
+        assert eng.stats()["fullsort_fallbacks"] == (0 if tweak == "none" else 1), tweak
+        # PRF on, with the re-query weight at 0 so that R = 0.7 * final keeps the crafted gaps
+        eng = install(idx, prf_mode="stored_rows", reranked_score_weight=0.0)
+        webui_api.RERANKED_SCORE_WEIGHT = 0.0
+        try:
+            P = port.OraclePort(idx)
+            P.consts["RERANKED_SCORE_WEIGHT"] = 0.0
+            eng.reset_stats()
+            assert_same(capture(webui_api.get_doc2vec_based_reranked_scores, f, 40), capture(P.rerank, f, 40), tweak)
+            assert eng.stats()["fullsort_fallbacks"] == (0 if tweak == "none" else 1), tweak
+        finally:
+            webui_api.RERANKED_SCORE_WEIGHT = 0.3
