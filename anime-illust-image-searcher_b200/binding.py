@@ -74,7 +74,8 @@ SIGNATURES = {
     "ais_stage_set_status": (C.c_int, [_vp, _i32, _vp]),
     "ais_stage_requery": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "ais_stage_requery_select": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
-    "ais_stage_finish": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "ais_stage_finish": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ais_stage_witness": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "ais_stage_export_keys": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "ais_stage_sort_finish": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "ais_max_select_k": (C.c_int, []),

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include "select.cuh"
+#include "select2.cuh"
 
 using namespace ais;
 
@@ -95,6 +96,24 @@ __global__ void keys_from_scores_kernel(const double* scores, int64_t n, uint64_
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = dkey(scores[i]);
 }
+// a single sorted candidate list per query: "merging" is a copy plus a count of the live entries
+__global__ void copy_list_kernel(const uint64_t* keys, const int64_t* ids, int k, uint64_t* out_keys, int64_t* out_ids,
+                                 int32_t* out_count) {
+    const int qi = blockIdx.x;
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t kk = keys[(size_t)qi * k + i];
+        out_keys[(size_t)qi * k + i] = kk;
+        out_ids[(size_t)qi * k + i] = ids[(size_t)qi * k + i];
+        mine += kk != KEY_EMPTY;
+    }
+    if (mine) atomicAdd(&cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && out_count) out_count[qi] = cnt;
+}
 __global__ void fill_empty_kernel(uint64_t* keys, int64_t* ids, int64_t lo, int64_t hi) {
     const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < hi) { keys[i] = KEY_EMPTY; ids[i] = ID_EMPTY; }
@@ -125,6 +144,8 @@ struct ais_engine {
     Buf blk_keys, blk_ids, grp_keys, grp_ids, cand_keys, cand_ids, rest_keys, rest_ids, rest_count;
     Buf out_ids, out_scores, out_count, out_amb;
     Buf fs_keys, fs_ids, fs_count;
+    Buf seg_max, sel_thr, surv_count, surv_keys, surv_ids, gate, witness, last_keys, wit_table;
+    uint64_t* h_last_keys = nullptr;
     int sel_k_cap = 0, out_topn_cap = 0;
     int cur_nq = 0;
     bool cur_prf = false;      // second pass ran for the current batch
@@ -210,15 +231,24 @@ int ensure_work(ais_engine* e) {
     TRY(dev_alloc(e, e->rows_own, (size_t)q * MAX_DEPTH * DIM * sizeof(float)));
     TRY(dev_alloc(e, e->out_count, (size_t)q * sizeof(int32_t)));
     TRY(dev_alloc(e, e->out_amb, (size_t)q * sizeof(int32_t)));
+    TRY(dev_alloc(e, e->seg_max, (size_t)q * SEG_MAX * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->sel_thr, (size_t)q * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->surv_count, (size_t)q * sizeof(int)));
+    TRY(dev_alloc(e, e->surv_keys, (size_t)q * SURV_CAP * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->surv_ids, (size_t)q * SURV_CAP * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->gate, (size_t)q * sizeof(int)));
+    TRY(dev_alloc(e, e->witness, (size_t)q * sizeof(int32_t)));
+    TRY(dev_alloc(e, e->last_keys, (size_t)q * sizeof(uint64_t)));
     if (q > e->qt_cap) {
         if (e->h_q) { cudaFreeHost(e->h_q); cudaFreeHost(e->h_qt); cudaFreeHost(e->h_q2); cudaFreeHost(e->h_top_ids);
-                      cudaFreeHost(e->h_top_scores); cudaFreeHost(e->h_small); }
+                      cudaFreeHost(e->h_top_scores); cudaFreeHost(e->h_small); cudaFreeHost(e->h_last_keys); }
         CK(cudaMallocHost((void**)&e->h_q, (size_t)q * DIM * sizeof(float)));
         CK(cudaMallocHost((void**)&e->h_q2, (size_t)q * DIM * sizeof(float)));
         CK(cudaMallocHost((void**)&e->h_qt, (size_t)q * sizeof(QueryTerms)));
         CK(cudaMallocHost((void**)&e->h_top_ids, (size_t)q * MAX_DEPTH * sizeof(int64_t)));
         CK(cudaMallocHost((void**)&e->h_top_scores, (size_t)q * MAX_DEPTH * sizeof(double)));
         CK(cudaMallocHost((void**)&e->h_small, (size_t)q * 3 * sizeof(int32_t)));
+        CK(cudaMallocHost((void**)&e->h_last_keys, (size_t)q * sizeof(uint64_t)));
         e->sel_k_cap = 0;       // candidate buffers are sized per query too
         e->out_topn_cap = 0;
     }
@@ -307,6 +337,7 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<4>()));
     CK(cudaFuncSetAttribute(scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<8>()));
     CK(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<16>()));
+    CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
     return AIS_OK;
 }
 
@@ -347,25 +378,91 @@ int launch_bm25(ais_engine* e, int nq) {
 
 // two-level merge of candidate lists into out[nq][k_out] (sorted best first, KEY_EMPTY padded)
 int merge_lists(ais_engine* e, const uint64_t* keys, const int64_t* ids, int n_lists, int64_t list_stride,
-                int64_t q_stride, int k_in, int k_out, int nq, uint64_t* out_keys, int64_t* out_ids, int32_t* out_count) {
+                int64_t q_stride, int k_in, int k_out, int nq, uint64_t* out_keys, int64_t* out_ids, int32_t* out_count,
+                const int* gate = nullptr) {
     if (n_lists > 2 * MERGE_GROUP) {
         const int ng = merge_groups(n_lists);
         if ((size_t)e->qt_cap * ng * k_out * sizeof(uint64_t) > e->grp_keys.cap)
             return fail(AIS_ERR_INVALID, "too many candidate lists to merge (%d)", n_lists);
         merge_kernel<<<dim3(ng, nq), SEL_THREADS, 0, e->stream>>>(keys, ids, n_lists, MERGE_GROUP, list_stride, q_stride,
                                                                  k_in, k_out, e->grp_keys.as<uint64_t>(),
-                                                                 e->grp_ids.as<int64_t>(), k_out, nullptr);
+                                                                 e->grp_ids.as<int64_t>(), k_out, nullptr, gate);
         LAUNCHED(e);
         merge_kernel<<<dim3(1, nq), SEL_THREADS, 0, e->stream>>>(e->grp_keys.as<uint64_t>(), e->grp_ids.as<int64_t>(), ng, ng,
                                                                 k_out, (int64_t)ng * k_out, k_out, k_out, out_keys, out_ids,
-                                                                k_out, out_count);
+                                                                k_out, out_count, gate);
         LAUNCHED(e);
     } else {
         merge_kernel<<<dim3(1, nq), SEL_THREADS, 0, e->stream>>>(keys, ids, n_lists, n_lists, list_stride, q_stride, k_in,
-                                                                k_out, out_keys, out_ids, k_out, out_count);
+                                                                k_out, out_keys, out_ids, k_out, out_count, gate);
         LAUNCHED(e);
     }
     return AIS_OK;
+}
+
+// Exact local top-k of one scoring stage -> out[nq][k] (sorted best first, KEY_EMPTY padded).
+//   mode 0: combine sim + bm25 (stores the combined scores), 1: stored combined scores, 2: PRF blend.
+// Fast path: segment maxima -> threshold -> collect -> sort (select2.cuh); the buffer-based kernels of
+// select.cuh follow, gated per query on the overflow flag the fast path raises.
+int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, uint64_t* d_keys, int64_t* d_ids) {
+    if (k < 1 || k > SEL_KMAX) return fail(AIS_ERR_INVALID, "k %d outside [1, %d]", k, SEL_KMAX);
+    TRY(ensure_sel(e, k));
+    const int64_t n = e->n();
+    SelectArgs a;
+    a.sim = e->sim.as<float>(); a.bm25 = e->bm25.as<double>(); a.fin = e->fin.as<double>(); a.rer = e->rer.as<float>();
+    a.n = n; a.ld = e->ld; a.id_base = e->first_doc;
+    a.cp = combine_params(e);
+    a.maxes = d_maxes;
+    a.seeds_all = e->top_ids.as<int64_t>();
+    a.depth = e->p.prf_depth;
+    a.mode = mode;
+    int64_t S = (n + 31) / 32;
+    if (S > SEG_MAX) S = SEG_MAX;
+    a.n_seg = (int)S;
+    a.seg_len = S > 0 ? (n + S - 1) / S : 0;
+    a.seg_max = e->seg_max.as<uint64_t>();
+    a.max_all = mode == 2 ? e->maxr_key.as<uint64_t>() : nullptr;
+    a.thr = e->sel_thr.as<uint64_t>();
+    a.surv_count = e->surv_count.as<int>();
+    a.surv_keys = e->surv_keys.as<uint64_t>();
+    a.surv_ids = e->surv_ids.as<int64_t>();
+    a.gate = e->gate.as<int>();
+    if (n > 0) {
+        const dim3 g1((unsigned)((S + SEG_WARPS - 1) / SEG_WARPS), (unsigned)nq);
+        if (mode == 0) segmax_kernel<0><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
+        else if (mode == 1) segmax_kernel<1><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
+        else segmax_kernel<2><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
+        LAUNCHED(e);
+    }
+    threshold_kernel<<<nq, 256, 0, e->stream>>>(a.seg_max, a.n_seg, k, a.thr, a.surv_count, a.gate);
+    LAUNCHED(e);
+    if (n > 0) {
+        int64_t cb = (n + COLLECT_THREADS * 8 - 1) / (COLLECT_THREADS * 8);
+        if (cb > 8LL * e->sm_count) cb = 8LL * e->sm_count;
+        const dim3 g3((unsigned)cb, (unsigned)nq);
+        if (mode == 2) collect_kernel<2><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        else collect_kernel<1><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        LAUNCHED(e);
+    }
+    sort_survivors_kernel<<<nq, 512, SURV_CAP * 16, e->stream>>>(a.surv_count, a.surv_keys, a.surv_ids, k, d_keys, d_ids, a.gate);
+    LAUNCHED(e);
+    // gated fallback (runs only for queries whose survivors overflowed)
+    const int G = sel_blocks(e);
+    const int* gate = e->gate.as<int>();
+    if (mode == 0)
+        combine_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
+            e->sim.as<float>(), e->bm25.as<double>(), e->fin.as<double>(), n, e->ld, d_maxes, a.cp, e->first_doc, k,
+            e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
+    else if (mode == 1)
+        final_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(e->fin.as<double>(), n, e->ld, e->first_doc, k,
+                                                                       e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
+    else
+        rerank_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
+            e->fin.as<double>(), e->rer.as<float>(), n, e->ld, a.cp, e->first_doc, e->top_ids.as<int64_t>(), e->p.prf_depth, k,
+            e->maxr_key.as<uint64_t>(), e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
+    LAUNCHED(e);
+    return merge_lists(e, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), G, k, (int64_t)G * k, k, k, nq, d_keys, d_ids,
+                       nullptr, gate);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -388,19 +485,7 @@ int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
 
 // from_final: select straight from e->fin (ais_rerank); else combine sim + bm25 first
 int do_combine(ais_engine* e, int nq, const double* d_maxes, int k, uint64_t* d_keys, int64_t* d_ids, bool from_final) {
-    if (k < 1 || k > SEL_KMAX) return fail(AIS_ERR_INVALID, "k %d outside [1, %d]", k, SEL_KMAX);
-    TRY(ensure_sel(e, k));
-    const int G = sel_blocks(e);
-    if (from_final)
-        final_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(e->fin.as<double>(), e->n(), e->ld, e->first_doc, k,
-                                                                       e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>());
-    else
-        combine_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
-            e->sim.as<float>(), e->bm25.as<double>(), e->fin.as<double>(), e->n(), e->ld, d_maxes, combine_params(e),
-            e->first_doc, k, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>());
-    LAUNCHED(e);
-    return merge_lists(e, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), G, k, (int64_t)G * k, k, k, nq, d_keys,
-                       d_ids, nullptr);
+    return local_select(e, from_final ? 1 : 0, nq, d_maxes, k, d_keys, d_ids);
 }
 
 int do_top(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys, const int64_t* d_ids, int64_t* out_top_ids,
@@ -440,16 +525,8 @@ int do_top(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys, co
 }
 
 int do_requery_select(ais_engine* e, int nq, int k, uint64_t* d_keys, int64_t* d_ids) {
-    if (k < 1 || k > SEL_KMAX) return fail(AIS_ERR_INVALID, "k %d outside [1, %d]", k, SEL_KMAX);
-    TRY(ensure_sel(e, k));
-    const int G = sel_blocks(e);
     // the max is re-accumulated (idempotent under atomicMax)
-    rerank_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
-        e->fin.as<double>(), e->rer.as<float>(), e->n(), e->ld, combine_params(e), e->first_doc, e->top_ids.as<int64_t>(),
-        e->p.prf_depth, k, e->maxr_key.as<uint64_t>(), e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>());
-    LAUNCHED(e);
-    return merge_lists(e, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), G, k, (int64_t)G * k, k, k, nq, d_keys,
-                       d_ids, nullptr);
+    return local_select(e, 2, nq, nullptr, k, d_keys, d_ids);
 }
 
 int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows, int prf_mode, int k, double* d_max_r,
@@ -484,14 +561,16 @@ int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows,
 }
 
 int copy_results(ais_engine* e, int nq, int topn, int64_t* out_ids, double* out_scores, int32_t* out_counts,
-                 int32_t* out_status, int32_t* out_amb) {
+                 int32_t* out_status, int32_t* out_amb, uint64_t* out_last_keys) {
     CK(cudaMemcpyAsync(e->h_out_ids, e->out_ids.p, (size_t)nq * topn * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(e->h_out_scores, e->out_scores.p, (size_t)nq * topn * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(e->h_small, e->out_count.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(e->h_small + e->qt_cap, e->status.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(e->h_small + 2 * e->qt_cap, e->out_amb.p, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_last_keys, e->last_keys.p, (size_t)nq * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     for (int q = 0; q < nq; ++q) {
+        if (out_last_keys) out_last_keys[q] = e->h_last_keys[q];
         const int st = e->h_small[e->qt_cap + q];
         const int cnt = st == AIS_Q_OK ? e->h_small[q] : 0;
         if (out_counts) out_counts[q] = cnt;
@@ -505,12 +584,19 @@ int copy_results(ais_engine* e, int nq, int topn, int64_t* out_ids, double* out_
 
 // d_max_r == NULL: the no-PRF branch (webui.py:247-253) - candidates are sorted finals, no pinned docs
 int do_finish(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys, const int64_t* d_ids, const double* d_max_r,
-              int topn, int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status, int32_t* out_amb) {
+              const int32_t* d_witness, int topn, int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status,
+              int32_t* out_amb, uint64_t* out_last_keys) {
     if (topn < 1) return fail(AIS_ERR_INVALID, "topn must be >= 1");
     TRY(ensure_sel(e, k));
     TRY(ensure_out(e, topn));
-    TRY(merge_lists(e, d_keys, d_ids, n_lists, (int64_t)nq * k, k, k, k, nq, e->rest_keys.as<uint64_t>(),
-                    e->rest_ids.as<int64_t>(), e->rest_count.as<int32_t>()));
+    if (n_lists == 1) {
+        copy_list_kernel<<<nq, 128, 0, e->stream>>>(d_keys, d_ids, k, e->rest_keys.as<uint64_t>(), e->rest_ids.as<int64_t>(),
+                                                   e->rest_count.as<int32_t>());
+        LAUNCHED(e);
+    } else {
+        TRY(merge_lists(e, d_keys, d_ids, n_lists, (int64_t)nq * k, k, k, k, nq, e->rest_keys.as<uint64_t>(),
+                        e->rest_ids.as<int64_t>(), e->rest_count.as<int32_t>()));
+    }
     TailParams tp;
     tp.thresh = e->p.diff_filter_thresh;
     tp.topn = topn;
@@ -519,10 +605,47 @@ int do_finish(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys,
     tp.n_total = e->total();
     tail_kernel<<<nq, SEL_THREADS, 0, e->stream>>>(e->rest_keys.as<uint64_t>(), e->rest_ids.as<int64_t>(), k,
                                                   e->rest_count.as<int32_t>(), nullptr, e->top_ids.as<int64_t>(), d_max_r, tp,
-                                                  e->out_ids.as<int64_t>(), e->out_scores.as<double>(),
-                                                  e->out_count.as<int32_t>(), e->out_amb.as<int32_t>());
+                                                  d_witness, e->out_ids.as<int64_t>(), e->out_scores.as<double>(),
+                                                  e->out_count.as<int32_t>(), e->out_amb.as<int32_t>(), e->last_keys.as<uint64_t>());
     LAUNCHED(e);
-    return copy_results(e, nq, topn, out_ids, out_scores, out_counts, out_status, out_amb);
+    return copy_results(e, nq, topn, out_ids, out_scores, out_counts, out_status, out_amb, out_last_keys);
+}
+
+constexpr int64_t WITNESS_BUCKETS = 1LL << 22;
+
+// For every ambiguous query: is there a pair of distinct scores closer than the threshold anywhere at or
+// below the last prefix entry?  d_witness[q] = 1 if this shard holds such a pair (sufficient, not necessary).
+int do_witness(ais_engine* e, int nq, const int32_t* amb, const uint64_t* last_keys, int second_pass, const double* d_max_r,
+               int32_t* d_witness) {
+    CK(cudaMemsetAsync(d_witness, 0, (size_t)nq * sizeof(int32_t), e->stream));
+    if (e->n() == 0) return AIS_OK;
+    TRY(dev_alloc(e, e->wit_table, (size_t)WITNESS_BUCKETS * sizeof(uint64_t)));
+    for (int q = 0; q < nq; ++q) {
+        if (!amb[q]) continue;
+        CK(cudaMemsetAsync(e->wit_table.p, 0, (size_t)WITNESS_BUCKETS * sizeof(uint64_t), e->stream));
+        WitnessArgs a;
+        a.fin = e->fin.as<double>() + (size_t)q * e->ld;
+        a.rer = e->rer.as<float>() + (size_t)q * e->ld;
+        a.n = e->n();
+        a.id_base = e->first_doc;
+        a.cp = combine_params(e);
+        a.second_pass = second_pass ? 1 : 0;
+        a.seeds = e->top_ids.as<int64_t>() + (size_t)q * MAX_DEPTH;
+        a.depth = e->p.prf_depth;
+        a.last_key = last_keys[q];
+        a.max_r = d_max_r ? d_max_r + q : nullptr;
+        a.normalize = d_max_r ? 1 : 0;
+        a.thresh = e->p.diff_filter_thresh;
+        a.inv_thresh = 1.0 / e->p.diff_filter_thresh;
+        a.table = e->wit_table.as<uint64_t>();
+        a.n_buckets = WITNESS_BUCKETS;
+        a.flag = d_witness + q;
+        int64_t blocks = (e->n() + 256 * 8 - 1) / (256 * 8);
+        if (blocks > 8LL * e->sm_count) blocks = 8LL * e->sm_count;
+        witness_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(a);
+        LAUNCHED(e);
+    }
+    return AIS_OK;
 }
 
 int64_t sort_capacity(int64_t n) {
@@ -582,9 +705,9 @@ int do_sort_finish(ais_engine* e, int qi, uint64_t* d_keys, int64_t* d_ids, int6
     // single-query launch: offset every per-query array to qi
     tail_kernel<<<1, SEL_THREADS, 0, e->stream>>>(d_keys, d_ids, 0, nullptr, e->fs_count.as<int64_t>(),
                                                  e->top_ids.as<int64_t>() + (size_t)qi * MAX_DEPTH,
-                                                 d_max_r ? d_max_r + qi : nullptr, tp, e->out_ids.as<int64_t>(),
+                                                 d_max_r ? d_max_r + qi : nullptr, tp, nullptr, e->out_ids.as<int64_t>(),
                                                  e->out_scores.as<double>(), e->out_count.as<int32_t>(),
-                                                 e->out_amb.as<int32_t>());
+                                                 e->out_amb.as<int32_t>(), nullptr);
     LAUNCHED(e);
     e->fullsort_fallbacks++;
     CK(cudaMemcpyAsync(e->h_out_ids, e->out_ids.p, (size_t)topn * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
@@ -629,17 +752,17 @@ int run_batch(ais_engine* e, const ais_query* qs, int q_index0, int nq, int topn
         TRY(ensure_sel(e, kk));
     }
 
+    std::vector<uint64_t> last_keys(nq, 0);
+    auto any_amb = [&]() { bool any = false; for (int q = 0; q < nq; ++q) any = any || amb[q]; return any; };
     if (!prf) {
-        int k = topn + 1 < SEL_KMAX ? topn + 1 : SEL_KMAX;
-        for (;;) {
-            TRY(do_combine(e, nq, maxes, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), qs == nullptr));
-            TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), nullptr, topn, out_ids,
-                          out_scores, out_counts, out_status, amb.data()));
-            bool any = false;
-            for (int q = 0; q < nq; ++q) any = any || amb[q];
-            if (!any || k == SEL_KMAX) break;
-            k = SEL_KMAX;
-            TRY(ensure_sel(e, k));
+        const int k = topn + 1 < SEL_KMAX ? topn + 1 : SEL_KMAX;
+        TRY(do_combine(e, nq, maxes, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), qs == nullptr));
+        TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), nullptr, nullptr, topn, out_ids,
+                      out_scores, out_counts, out_status, amb.data(), last_keys.data()));
+        if (any_amb()) {       // one near-tie inside the prefix: look for a second one anywhere below it
+            TRY(do_witness(e, nq, amb.data(), last_keys.data(), 0, nullptr, e->witness.as<int32_t>()));
+            TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), nullptr, e->witness.as<int32_t>(),
+                          topn, out_ids, out_scores, out_counts, out_status, amb.data(), nullptr));
         }
     } else {
         TRY(do_combine(e, nq, maxes, depth, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), qs == nullptr));
@@ -678,15 +801,12 @@ int run_batch(ais_engine* e, const ais_query* qs, int q_index0, int nq, int topn
         double* maxr = e->maxr_own.as<double>();
         TRY(do_requery(e, nq, host_q2 ? q2.data() : nullptr, host_q2 ? nullptr : e->rows_own.as<float>(), prf_mode, k, maxr,
                        e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>()));
-        for (;;) {
-            TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), maxr, topn, out_ids, out_scores,
-                          out_counts, out_status, amb.data()));
-            bool any = false;
-            for (int q = 0; q < nq; ++q) any = any || amb[q];
-            if (!any || k == SEL_KMAX) break;
-            k = SEL_KMAX;
-            TRY(ensure_sel(e, k));
-            TRY(do_requery_select(e, nq, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>()));
+        TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), maxr, nullptr, topn, out_ids, out_scores,
+                      out_counts, out_status, amb.data(), last_keys.data()));
+        if (any_amb()) {
+            TRY(do_witness(e, nq, amb.data(), last_keys.data(), 1, maxr, e->witness.as<int32_t>()));
+            TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), maxr, e->witness.as<int32_t>(), topn,
+                          out_ids, out_scores, out_counts, out_status, amb.data(), nullptr));
         }
     }
     // exact fallback: the filter outcome depends on scores beyond the SEL_KMAX best -> sort everything
@@ -778,10 +898,11 @@ int ais_destroy(ais_engine* e) {
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
-                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count})
+                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->sel_thr, &e->surv_count,
+                   &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,
-                    (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small})
+                    (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small, (void*)e->h_last_keys})
         if (h) cudaFreeHost(h);
     for (cudaEvent_t ev : e->ev_pending) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_free) cudaEventDestroy(ev);
@@ -1006,8 +1127,8 @@ int ais_filter_sorted(ais_engine* e, const int64_t* ids, const double* scores, i
         tp.normalize = 0;
         tp.n_total = n;
         tail_kernel<<<1, SEL_THREADS, 0, e->stream>>>(e->fs_keys.as<uint64_t>(), e->fs_ids.as<int64_t>(), 0, nullptr,
-                                                     e->fs_count.as<int64_t>(), nullptr, nullptr, tp, d_oi.as<int64_t>(),
-                                                     d_os.as<double>(), e->out_count.as<int32_t>(), e->out_amb.as<int32_t>());
+                                                     e->fs_count.as<int64_t>(), nullptr, nullptr, tp, nullptr, d_oi.as<int64_t>(),
+                                                     d_os.as<double>(), e->out_count.as<int32_t>(), e->out_amb.as<int32_t>(), nullptr);
         LAUNCHED(e);
         int32_t cnt = 0;
         CK(cudaMemcpyAsync(&cnt, e->out_count.p, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -1067,13 +1188,20 @@ int ais_stage_requery_select(ais_engine* e, int32_t nq, int32_t k, uint64_t* d_c
     return do_requery_select(e, nq, k, d_cand_keys, d_cand_ids);
 }
 int ais_stage_finish(ais_engine* e, int32_t nq, int32_t n_lists, int32_t k, const uint64_t* d_cand_keys, const int64_t* d_cand_ids,
-                     const double* d_max_r, int32_t topn, int64_t* out_ids, double* out_scores, int32_t* out_counts,
-                     int32_t* out_status, int32_t* out_ambiguous) {
+                     const double* d_max_r, const int32_t* d_witness, int32_t topn, int64_t* out_ids, double* out_scores,
+                     int32_t* out_counts, int32_t* out_status, int32_t* out_ambiguous, uint64_t* out_last_keys) {
     if (!e || !d_cand_keys || !d_cand_ids || n_lists < 1) return fail(AIS_ERR_INVALID, "bad argument");
     if (nq != e->cur_nq) return fail(AIS_ERR_INVALID, "nq %d differs from the scored batch (%d)", nq, e->cur_nq);
     DeviceGuard g(e->device);
-    return do_finish(e, nq, n_lists, k, d_cand_keys, d_cand_ids, d_max_r, topn, out_ids, out_scores, out_counts, out_status,
-                     out_ambiguous);
+    return do_finish(e, nq, n_lists, k, d_cand_keys, d_cand_ids, d_max_r, d_witness, topn, out_ids, out_scores, out_counts,
+                     out_status, out_ambiguous, out_last_keys);
+}
+int ais_stage_witness(ais_engine* e, int32_t nq, const int32_t* ambiguous, const uint64_t* last_keys, int32_t second_pass,
+                      const double* d_max_r, int32_t* d_witness) {
+    if (!e || !ambiguous || !last_keys || !d_witness) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (nq != e->cur_nq) return fail(AIS_ERR_INVALID, "nq %d differs from the scored batch (%d)", nq, e->cur_nq);
+    DeviceGuard g(e->device);
+    return do_witness(e, nq, ambiguous, last_keys, second_pass, d_max_r, d_witness);
 }
 int ais_stage_export_keys(ais_engine* e, int32_t query, int32_t second_pass, uint64_t* d_keys, int64_t* d_ids) {
     if (!e || !d_keys || !d_ids || query < 0 || query >= e->cur_nq) return fail(AIS_ERR_INVALID, "bad argument");

@@ -175,9 +175,10 @@ struct CombineF {
 __global__ void __launch_bounds__(SEL_THREADS)
 combine_select_kernel(const float* __restrict__ sim, const double* __restrict__ bm25, double* __restrict__ final_out,
                       int64_t n, int64_t ld, const double* __restrict__ maxes, CombineParams cp, int64_t id_base,
-                      int k, uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids) {
+                      int k, uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids, const int* __restrict__ gate) {
     __shared__ SelBuf sb;
     const int qi = blockIdx.y;
+    if (gate && !gate[qi]) return;          // only runs when the streaming select overflowed (select2.cuh)
     const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * chunk;
     const int64_t hi = lo + chunk < n ? lo + chunk : n;
@@ -201,9 +202,10 @@ struct FinalF {
 };
 __global__ void __launch_bounds__(SEL_THREADS)
 final_select_kernel(const double* __restrict__ fin, int64_t n, int64_t ld, int64_t id_base, int k,
-                    uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids) {
+                    uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids, const int* __restrict__ gate) {
     __shared__ SelBuf sb;
     const int qi = blockIdx.y;
+    if (gate && !gate[qi]) return;
     const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * chunk;
     const int64_t hi = lo + chunk < n ? lo + chunk : n;
@@ -240,11 +242,13 @@ struct RerankF {
 __global__ void __launch_bounds__(SEL_THREADS)
 rerank_select_kernel(const double* __restrict__ fin, const float* __restrict__ rer, int64_t n, int64_t ld,
                      CombineParams cp, int64_t id_base, const int64_t* __restrict__ top_ids_all, int depth, int k,
-                     uint64_t* __restrict__ max_keys, uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids) {
+                     uint64_t* __restrict__ max_keys, uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids,
+                     const int* __restrict__ gate) {
     __shared__ SelBuf sb;
     __shared__ int64_t top_ids[MAX_DEPTH];
     __shared__ uint64_t wscratch[SEL_THREADS / 32];
     const int qi = blockIdx.y;
+    if (gate && !gate[qi]) return;
     const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * chunk;
     const int64_t hi = lo + chunk < n ? lo + chunk : n;
@@ -283,9 +287,10 @@ __global__ void __launch_bounds__(SEL_THREADS)
 merge_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ ids, int n_lists, int group,
              int64_t list_stride, int64_t q_stride, int k_in, int k_out,
              uint64_t* __restrict__ out_keys, int64_t* __restrict__ out_ids, int64_t out_stride,
-             int32_t* __restrict__ out_count) {
+             int32_t* __restrict__ out_count, const int* __restrict__ gate) {
     __shared__ SelBuf sb;
     const int g = blockIdx.x, qi = blockIdx.y;
+    if (gate && !gate[qi]) return;
     const int list0 = g * group;
     const int my_lists = (n_lists - list0 < group) ? (n_lists - list0) : group;
     sel_init(sb);
@@ -424,8 +429,9 @@ __global__ void __launch_bounds__(SEL_THREADS)
 tail_kernel(const uint64_t* __restrict__ rest_keys_all, const int64_t* __restrict__ rest_ids_all, int64_t rest_stride,
             const int32_t* __restrict__ rest_count, const int64_t* __restrict__ rest_count64,
             const int64_t* __restrict__ top_ids_all, const double* __restrict__ max_r_all, TailParams tp,
+            const int32_t* __restrict__ witness,      // nullable; [q] = 1: a near-tie is known to exist below the prefix
             int64_t* __restrict__ out_ids, double* __restrict__ out_scores, int32_t* __restrict__ out_count,
-            int32_t* __restrict__ out_ambiguous) {
+            int32_t* __restrict__ out_ambiguous, uint64_t* __restrict__ out_last_key) {
     __shared__ unsigned long long s_first, s_second, s_nonpos;
     const int qi = blockIdx.x, tid = threadIdx.x;
     const uint64_t* rest_keys = rest_keys_all + (size_t)qi * rest_stride;
@@ -476,7 +482,7 @@ tail_kernel(const uint64_t* __restrict__ rest_keys_all, const int64_t* __restric
     if (second != INF) t = (int64_t)second;                       // webui.py:76-77
     else if (first != INF) {
         if (complete) t = (int64_t)first;                         // webui.py:74-75
-        else { t = lim; ambiguous = (int64_t)first < npos; }      // a 2nd point may exist beyond the prefix
+        else { t = lim; ambiguous = (int64_t)first < npos && !(witness && witness[qi]); }   // a 2nd point may exist beyond the prefix
     } else t = complete ? len : lim;
     int64_t cnt = t < npos ? t : npos;
     if (cnt > lim) cnt = lim;
@@ -490,6 +496,7 @@ tail_kernel(const uint64_t* __restrict__ rest_keys_all, const int64_t* __restric
     if (tid == 0) {
         out_count[qi] = (int32_t)cnt;
         out_ambiguous[qi] = ambiguous ? 1 : 0;
+        if (out_last_key) out_last_key[qi] = m > 0 ? rest_keys[m - 1] : ~0ull;
     }
 }
 

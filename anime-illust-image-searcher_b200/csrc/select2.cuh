@@ -1,0 +1,306 @@
+// Streaming threshold select (the fast path of the top-k stages) and the near-tie witness pass.
+//
+// Exact top-k of N keys in three light passes, none of which synchronises inside its loop:
+//   1. segmax:    the docs are cut into S <= 2048 contiguous segments; one warp per segment streams its
+//                 docs (computing the combined score on the fly) and records the segment's best key.
+//   2. threshold: T = k-th largest segment maximum.  At least k docs (one per such segment) have
+//                 key >= T, so the global top-k is contained in {key >= T}; with docs spread over the
+//                 segments |{key >= T}| ~ -S ln(1 - k/S), i.e. barely more than k.
+//   3. collect:   stream again, append every doc with key >= T to a survivor list (warp-aggregated
+//                 atomics), then ONE block sorts the survivors (key desc, doc id asc) and writes the top-k.
+// If the survivors exceed SURV_CAP (top docs clustered in few segments) the query's gate flag is raised
+// and the buffer-based kernels of select.cuh, launched right behind and gated on that flag, redo it.
+//
+// The witness pass settles filter_searched_result's "is there a second near-tie anywhere?" question
+//  without sorting: two DISTINCT scores closer than DIFF_FILTER_THRESH anywhere below the
+// returned prefix imply an adjacent near-tie there, and two such scores falling into one bucket of width
+// thresh are found with a single atomicMax per doc.
+#pragma once
+#include "select.cuh"
+
+namespace ais {
+
+constexpr int SEG_MAX = 2048;            // segments per query
+constexpr int SEG_WARPS = 8;             // warps (= segments) per block
+constexpr int SEG_MIN_DOCS = 64;
+constexpr int SURV_CAP = 4096;
+constexpr int COLLECT_THREADS = 256;
+
+// ---- score functors: key of doc i, false if the doc is not a candidate ---------------------------
+struct ScoreCombine {      // pass 1: webui.py:376-383, also stores the combined score
+    const float* sim; const double* bm25; double* fin; float maxs; double maxb; CombineParams cp;
+    __device__ __forceinline__ bool operator()(int64_t i, int64_t, uint64_t& key) const {
+        float s = sim[i];
+        double b = bm25[i];
+        if (maxs > 0.0f) s = __fdiv_rn(s, maxs);
+        if (maxb > 0.0) b = __ddiv_rn(b, maxb);
+        const double f = __dadd_rn(__dmul_rn(cp.wb, b), (double)__fmul_rn(cp.wd, s));
+        fin[i] = f;
+        key = dkey(f);
+        return true;
+    }
+};
+struct ScoreFinal {        // stored combined scores
+    const double* fin;
+    __device__ __forceinline__ bool operator()(int64_t i, int64_t, uint64_t& key) const {
+        key = dkey(fin[i]);
+        return true;
+    }
+};
+struct ScoreRerank {       // pass 2: webui.py:208 blend; the PRF seeds are not candidates (webui.py:217)
+    const double* fin; const float* rer; CombineParams cp; const int64_t* seeds; int depth;
+    __device__ __forceinline__ bool operator()(int64_t i, int64_t id, uint64_t& key) const {
+        const double r = __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)__fmul_rn(cp.wr, rer[i]));
+        key = dkey(r);
+        bool keep = true;
+        for (int t = 0; t < depth; ++t) keep = keep && (seeds[t] != id);
+        return keep;
+    }
+};
+
+struct SelectArgs {        // everything the three kernels share
+    const float* sim; const double* bm25; double* fin; const float* rer;
+    int64_t n, ld, id_base;
+    CombineParams cp;
+    const double* maxes;        // [nq][2] (mode 0)
+    const int64_t* seeds_all;   // [nq][MAX_DEPTH] (mode 2)
+    int depth;
+    int mode;                   // 0 combine (pass 1), 1 stored finals, 2 rerank blend (pass 2)
+    int n_seg; int64_t seg_len;
+    uint64_t* seg_max;          // [nq][SEG_MAX]
+    uint64_t* max_all;          // [nq] atomicMax over ALL docs (mode 2: max R) or null
+    uint64_t* thr;              // [nq]
+    int* surv_count;            // [nq]
+    uint64_t* surv_keys;        // [nq][SURV_CAP]
+    int64_t* surv_ids;
+    int* gate;                  // [nq] raised when the survivors overflow
+};
+
+template <int MODE, typename Body>
+__device__ __forceinline__ void with_functor(const SelectArgs& a, int qi, const int64_t* seeds_smem, Body&& body) {
+    if (MODE == 0) {
+        ScoreCombine f{a.sim + (size_t)qi * a.ld, a.bm25 + (size_t)qi * a.ld, a.fin + (size_t)qi * a.ld,
+                       (float)a.maxes[2 * qi + 1], a.maxes[2 * qi], a.cp};
+        body(f);
+    } else if (MODE == 1) {
+        ScoreFinal f{a.fin + (size_t)qi * a.ld};
+        body(f);
+    } else {
+        ScoreRerank f{a.fin + (size_t)qi * a.ld, a.rer + (size_t)qi * a.ld, a.cp, seeds_smem, a.depth};
+        body(f);
+    }
+}
+
+// ---- 1. segment maxima -----------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(32 * SEG_WARPS)
+segmax_kernel(SelectArgs a) {
+    __shared__ int64_t seeds[MAX_DEPTH];
+    __shared__ uint64_t wall[SEG_WARPS];
+    const int qi = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (MODE == 2) {
+        if (threadIdx.x < MAX_DEPTH) seeds[threadIdx.x] = a.seeds_all[qi * MAX_DEPTH + threadIdx.x];
+        __syncthreads();
+    }
+    const int seg = blockIdx.x * SEG_WARPS + warp;
+    uint64_t best = KEY_EMPTY, all_best = KEY_EMPTY;
+    if (seg < a.n_seg) {
+        const int64_t lo = (int64_t)seg * a.seg_len;
+        const int64_t hi = lo + a.seg_len < a.n ? lo + a.seg_len : a.n;
+        with_functor<MODE>(a, qi, seeds, [&](auto& f) {
+            int64_t i = lo + lane;
+#pragma unroll 1
+            for (; i + 96 < hi; i += 128) {
+                uint64_t k0, k1, k2, k3;
+                const bool o0 = f(i, a.id_base + i, k0);
+                const bool o1 = f(i + 32, a.id_base + i + 32, k1);
+                const bool o2 = f(i + 64, a.id_base + i + 64, k2);
+                const bool o3 = f(i + 96, a.id_base + i + 96, k3);
+                uint64_t m01 = k0 > k1 ? k0 : k1, m23 = k2 > k3 ? k2 : k3;
+                uint64_t m = m01 > m23 ? m01 : m23;
+                all_best = m > all_best ? m : all_best;
+                k0 = o0 ? k0 : KEY_EMPTY; k1 = o1 ? k1 : KEY_EMPTY; k2 = o2 ? k2 : KEY_EMPTY; k3 = o3 ? k3 : KEY_EMPTY;
+                m01 = k0 > k1 ? k0 : k1; m23 = k2 > k3 ? k2 : k3;
+                m = m01 > m23 ? m01 : m23;
+                best = m > best ? m : best;
+            }
+            for (; i < hi; i += 32) {
+                uint64_t k;
+                const bool ok = f(i, a.id_base + i, k);
+                all_best = k > all_best ? k : all_best;
+                if (ok) best = k > best ? k : best;
+            }
+        });
+        best = warp_max_u64(best);
+        if (lane == 0) a.seg_max[(size_t)qi * SEG_MAX + seg] = best;
+    }
+    if (a.max_all) {
+        all_best = warp_max_u64(all_best);
+        if (lane == 0) wall[warp] = all_best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t m = wall[0];
+            for (int w = 1; w < SEG_WARPS; ++w) m = wall[w] > m ? wall[w] : m;
+            if (m != KEY_EMPTY) atomicMax(reinterpret_cast<unsigned long long*>(&a.max_all[qi]), (unsigned long long)m);
+        }
+    }
+}
+
+// ---- 2. threshold = k-th largest segment maximum ------------------------------------------------------
+__global__ void __launch_bounds__(256)
+threshold_kernel(const uint64_t* __restrict__ seg_max, int n_seg, int k, uint64_t* __restrict__ thr,
+                 int* __restrict__ surv_count, int* __restrict__ gate) {
+    __shared__ uint64_t v[SEG_MAX];
+    const int qi = blockIdx.x, tid = threadIdx.x;
+    int P = 32;
+    while (P < n_seg) P <<= 1;
+    for (int i = tid; i < P; i += 256) v[i] = i < n_seg ? seg_max[(size_t)qi * SEG_MAX + i] : KEY_EMPTY;
+    __syncthreads();
+    for (unsigned size = 2; size <= (unsigned)P; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = tid; t < (unsigned)P / 2; t += 256) {
+                const unsigned i = 2 * t - (t & (stride - 1));
+                const unsigned l = i + stride;
+                const bool up = ((i & size) == 0);
+                const uint64_t x = v[i], y = v[l];
+                if ((y > x) == up) { v[i] = y; v[l] = x; }       // descending
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        uint64_t t = (k <= P) ? v[k - 1] : KEY_EMPTY;
+        thr[qi] = t != KEY_EMPTY ? t : 1ull;          // fewer than k non-empty segments: every doc qualifies
+        surv_count[qi] = 0;
+        gate[qi] = 0;
+    }
+}
+
+// ---- 3a. collect the survivors -------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(COLLECT_THREADS)
+collect_kernel(SelectArgs a) {
+    __shared__ int64_t seeds[MAX_DEPTH];
+    const int qi = blockIdx.y, lane = threadIdx.x & 31;
+    if (MODE == 2) {
+        if (threadIdx.x < MAX_DEPTH) seeds[threadIdx.x] = a.seeds_all[qi * MAX_DEPTH + threadIdx.x];
+        __syncthreads();
+    }
+    const uint64_t T = a.thr[qi];
+    int* cnt = a.surv_count + qi;
+    uint64_t* sk = a.surv_keys + (size_t)qi * SURV_CAP;
+    int64_t* si = a.surv_ids + (size_t)qi * SURV_CAP;
+    const int64_t stride = (int64_t)gridDim.x * COLLECT_THREADS;
+    const int64_t n_round = ((a.n + 31) / 32) * 32;          // whole warps stay together for the ballots
+    with_functor<(MODE == 0 ? 1 : MODE)>(a, qi, seeds, [&](auto& f) {   // pass 1 re-reads the stored finals
+        for (int64_t i = (int64_t)blockIdx.x * COLLECT_THREADS + threadIdx.x; i < n_round; i += stride) {
+            uint64_t key = KEY_EMPTY;
+            bool pass = false;
+            if (i < a.n) pass = f(i, a.id_base + i, key) && key >= T;
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(cnt, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (pass) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < SURV_CAP) { sk[pos] = key; si[pos] = a.id_base + i; }
+                }
+            }
+        }
+    });
+}
+
+// ---- 3b. sort the survivors, write the top-k ---------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+sort_survivors_kernel(const int* __restrict__ surv_count, const uint64_t* __restrict__ surv_keys,
+                      const int64_t* __restrict__ surv_ids, int k, uint64_t* __restrict__ out_keys,
+                      int64_t* __restrict__ out_ids, int* __restrict__ gate) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint64_t* key = reinterpret_cast<uint64_t*>(sm);
+    int64_t* id = reinterpret_cast<int64_t*>(sm + (size_t)SURV_CAP * 8);
+    const int qi = blockIdx.x, tid = threadIdx.x;
+    const int cnt = surv_count[qi];
+    if (cnt > SURV_CAP) {                       // overflow: the gated buffer-select kernels take over
+        if (tid == 0) gate[qi] = 1;
+        return;
+    }
+    int P = 64;
+    while (P < cnt) P <<= 1;
+    for (int i = tid; i < P; i += 512) {
+        key[i] = i < cnt ? surv_keys[(size_t)qi * SURV_CAP + i] : KEY_EMPTY;
+        id[i] = i < cnt ? surv_ids[(size_t)qi * SURV_CAP + i] : ID_EMPTY;
+    }
+    __syncthreads();
+    for (unsigned size = 2; size <= (unsigned)P; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = tid; t < (unsigned)P / 2; t += 512) {
+                const unsigned i = 2 * t - (t & (stride - 1));
+                const unsigned l = i + stride;
+                const bool up = ((i & size) == 0);
+                const uint64_t ka = key[i], kb = key[l];
+                const int64_t ia = id[i], ib = id[l];
+                if (better(kb, ib, ka, ia) == up) { key[i] = kb; id[i] = ib; key[l] = ka; id[l] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < k; i += 512) {
+        const bool live = i < cnt && i < P;
+        out_keys[(size_t)qi * k + i] = live ? key[i] : KEY_EMPTY;
+        out_ids[(size_t)qi * k + i] = live ? id[i] : ID_EMPTY;
+    }
+}
+
+// ---- near-tie witness ------------------------------------------------------------------------------------
+struct WitnessArgs {
+    const double* fin; const float* rer;      // rows of the query
+    int64_t n, id_base;
+    CombineParams cp;
+    int second_pass;                          // 1: value = normalised blend R (seeds skipped); 0: combined score
+    const int64_t* seeds; int depth;
+    uint64_t last_key;                        // key of the last entry of the sorted prefix
+    const double* max_r; int normalize;          // device scalar (nullable)
+    double thresh, inv_thresh;
+    uint64_t* table; int64_t n_buckets;
+    int* flag;
+};
+
+__device__ __forceinline__ double witness_value(int normalize, double max_r, double raw) {
+    return (normalize && max_r > 0.0) ? __ddiv_rn(raw, max_r) : raw;             // webui.py:210-211
+}
+
+__global__ void __launch_bounds__(256)
+witness_kernel(WitnessArgs a) {
+    __shared__ int64_t seeds[MAX_DEPTH];
+    if (threadIdx.x < MAX_DEPTH) seeds[threadIdx.x] = (a.second_pass && threadIdx.x < a.depth) ? a.seeds[threadIdx.x] : -1;
+    __syncthreads();
+    const double max_r = a.max_r ? *a.max_r : 0.0;
+    const double v_last = a.last_key == ~0ull ? 1.0 : witness_value(a.normalize, max_r, dkey_inv(a.last_key));
+    const uint64_t neg_inf = dkey(-INFINITY);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        if (*((volatile int*)a.flag)) return;                   // somebody found one
+        double raw = a.fin[i];
+        if (a.second_pass) raw = __dadd_rn(__dmul_rn(a.cp.wo, raw), (double)__fmul_rn(a.cp.wr, a.rer[i]));
+        const uint64_t key = dkey(raw);
+        if (key > a.last_key || key <= neg_inf) continue;       // inside the prefix region / masked
+        const int64_t id = a.id_base + i;
+        bool seed = false;
+        for (int t = 0; t < MAX_DEPTH; ++t) seed = seed || (seeds[t] == id);
+        if (seed) continue;
+        const double v = witness_value(a.normalize, max_r, raw);
+        const double off = (v_last - v) * a.inv_thresh;
+        if (!(off >= 0.0) || off >= (double)a.n_buckets) continue;
+        const uint64_t vk = dkey(v);
+        const uint64_t old = atomicMax(reinterpret_cast<unsigned long long*>(&a.table[(int64_t)off]), (unsigned long long)vk);
+        if (old != KEY_EMPTY && old != vk) {
+            const double o = dkey_inv(old);
+            const double d = o > v ? __dsub_rn(o, v) : __dsub_rn(v, o);
+            if (d != 0.0 && d < a.thresh) atomicExch(a.flag, 1);
+        }
+    }
+}
+
+}  // namespace ais

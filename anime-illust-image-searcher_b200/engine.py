@@ -333,15 +333,23 @@ class SearchEngine:
     def stage_requery_select(self, nq: int, k: int, keys, ids) -> None:
         check(lib.ais_stage_requery_select(self._h, nq, k, _ptr(keys), _ptr(ids)))
 
-    def stage_finish(self, nq: int, n_lists: int, k: int, keys, ids, max_r, topn: int):
+    def stage_finish(self, nq: int, n_lists: int, k: int, keys, ids, max_r, topn: int, witness=None):
+        """-> (ids, scores, counts, status, ambiguous, last_keys)"""
         out_ids = np.zeros((nq, topn), dtype=np.int64)
         out_scores = np.zeros((nq, topn), dtype=np.float64)
         counts = np.zeros(nq, dtype=np.int32)
         status = np.zeros(nq, dtype=np.int32)
         amb = np.zeros(nq, dtype=np.int32)
-        check(lib.ais_stage_finish(self._h, nq, n_lists, k, _ptr(keys), _ptr(ids), _ptr(max_r), topn, _ptr(out_ids),
-                                   _ptr(out_scores), _ptr(counts), _ptr(status), _ptr(amb)))
-        return out_ids, out_scores, counts, status, amb
+        last = np.zeros(nq, dtype=np.uint64)
+        check(lib.ais_stage_finish(self._h, nq, n_lists, k, _ptr(keys), _ptr(ids), _ptr(max_r), _ptr(witness), topn,
+                                   _ptr(out_ids), _ptr(out_scores), _ptr(counts), _ptr(status), _ptr(amb), _ptr(last)))
+        return out_ids, out_scores, counts, status, amb, last
+
+    def stage_witness(self, amb: np.ndarray, last_keys: np.ndarray, second_pass: bool, max_r, witness) -> None:
+        amb = np.ascontiguousarray(amb, dtype=np.int32)
+        last_keys = np.ascontiguousarray(last_keys, dtype=np.uint64)
+        check(lib.ais_stage_witness(self._h, len(amb), _ptr(amb), _ptr(last_keys), 1 if second_pass else 0, _ptr(max_r),
+                                    _ptr(witness)))
 
     def stage_export_keys(self, query: int, second_pass: bool, keys, ids) -> None:
         check(lib.ais_stage_export_keys(self._h, query, 1 if second_pass else 0, _ptr(keys), _ptr(ids)))

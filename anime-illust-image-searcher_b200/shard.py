@@ -125,15 +125,11 @@ class ShardedSearch:
 
         if not prf:
             k = min(topn + 1, self.kmax)
-            while True:
-                keys, ids = self._cand_buffers(nq, k)
-                for e, m, kk, ii in zip(E, maxes_e, keys, ids):
-                    e.stage_combine(nq, m, k, kk, ii)
-                gk, gi = self._gather_lists(keys, ids)
-                res = E[0].stage_finish(nq, gk.shape[0], k, gk, gi, None, topn)
-                if not res[4].any() or k == self.kmax:
-                    break
-                k = self.kmax
+            keys, ids = self._cand_buffers(nq, k)
+            for e, m, kk, ii in zip(E, maxes_e, keys, ids):
+                e.stage_combine(nq, m, k, kk, ii)
+            gk, gi = self._gather_lists(keys, ids)
+            res = self._finish(nq, k, gk, gi, None, topn, second_pass=False)
             return self._resolve_ambiguous(res, nq, topn, None, second_pass=False) + (errors,)
 
         # --- PRF seeds: global top-`depth`
@@ -189,16 +185,25 @@ class ShardedSearch:
         for e, r, mr, kk, ii in zip(E, rows_e, maxr_l, keys, ids):
             e.stage_requery(nq, q2, r, prf_mode, k, mr, kk, ii)
         maxr = self.comm.all_max(self._reduce_local(maxr_l, torch.maximum))
-        while True:
-            gk, gi = self._gather_lists(keys, ids)
-            res = E[0].stage_finish(nq, gk.shape[0], k, gk, gi, maxr, topn)
-            if not res[4].any() or k == self.kmax:
-                break
-            k = self.kmax
-            keys, ids = self._cand_buffers(nq, k)
-            for e, kk, ii in zip(E, keys, ids):
-                e.stage_requery_select(nq, k, kk, ii)
+        gk, gi = self._gather_lists(keys, ids)
+        res = self._finish(nq, k, gk, gi, maxr, topn, second_pass=True)
         return self._resolve_ambiguous(res, nq, topn, maxr, second_pass=True) + (errors,)
+
+    def _finish(self, nq: int, k: int, gk, gi, maxr, topn: int, second_pass: bool):
+        """stage_finish on engine 0 (every rank holds identical inputs); an ambiguous filter outcome first
+        goes through the near-tie witness pass on every shard (flags all-reduced with MAX)."""
+        E = self.engines
+        res = E[0].stage_finish(nq, gk.shape[0], k, gk, gi, maxr, topn)
+        amb, last = res[4], res[5]
+        if amb.any():
+            flags = []
+            for e in E:
+                w = torch.zeros((nq,), dtype=torch.int32, device=self._dev(e))
+                e.stage_witness(amb, last, second_pass, None if maxr is None else maxr.to(self._dev(e)), w)
+                flags.append(w)
+            wit = self.comm.all_max(self._reduce_local(flags, torch.maximum))
+            res = E[0].stage_finish(nq, gk.shape[0], k, gk, gi, maxr, topn, witness=wit)
+        return res[:5]
 
     def _resolve_ambiguous(self, res, nq: int, topn: int, maxr, second_pass: bool):
         """Exact fallback: all-gather every shard's keys for the query and sort them (rare)."""

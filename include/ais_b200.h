@@ -191,12 +191,21 @@ int ais_stage_set_status(ais_engine* e, int32_t nq, const int32_t* status);
  * filter_searched_result and write the results (host arrays).  d_max_r == NULL selects the
  * no-PRF branch (webui.py:247-253): the candidates are the sorted combined scores of
  * ais_stage_combine and no docs are pinned.  A query whose filter outcome depends on scores
- * beyond the k candidates gets out_ambiguous[q] = 1: the caller repeats ais_stage_requery_select
- * (or ais_stage_combine) with k = ais_max_select_k(), and if still ambiguous sorts everything
- * with ais_stage_export_keys + ais_stage_sort_finish. */
+ * beyond the k candidates gets out_ambiguous[q] = 1: the caller runs ais_stage_witness, repeats this
+ * call with the witness flags, and sorts everything (ais_stage_export_keys + ais_stage_sort_finish)
+ * for the queries that are still ambiguous. */
 int ais_stage_finish(ais_engine* e, int32_t nq, int32_t n_lists, int32_t k, const uint64_t* d_cand_keys,
-                     const int64_t* d_cand_ids, const double* d_max_r, int32_t topn, int64_t* out_ids,
-                     double* out_scores, int32_t* out_counts, int32_t* out_status, int32_t* out_ambiguous);
+                     const int64_t* d_cand_ids, const double* d_max_r, const int32_t* d_witness /* nullable */,
+                     int32_t topn, int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status,
+                     int32_t* out_ambiguous, uint64_t* out_last_keys /* nullable, [nq] */);
+/* Cheap resolution of an ambiguous outcome: for every query with ambiguous[q] != 0 (host array) look, on
+ * this shard, for two DISTINCT scores closer than DIFF_FILTER_THRESH at or below the last entry of the
+ * sorted prefix (last_keys[q], host array as returned by ais_stage_finish) - such a pair implies an adjacent
+ * near-tie below the prefix.  d_witness [nq] (device, int32) is set to 1 where one is found; the caller
+ * all-reduces it (MAX) and repeats ais_stage_finish with it.  Sufficient, not necessary: a query that
+ * stays ambiguous goes to the full sort below. */
+int ais_stage_witness(ais_engine* e, int32_t nq, const int32_t* ambiguous, const uint64_t* last_keys,
+                      int32_t second_pass, const double* d_max_r, int32_t* d_witness);
 /* re-select second-pass candidates with another k without re-scanning (k <= ais_max_select_k()). */
 int ais_stage_requery_select(ais_engine* e, int32_t nq, int32_t k, uint64_t* d_cand_keys, int64_t* d_cand_ids);
 int ais_max_select_k(void);

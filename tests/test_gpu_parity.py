@@ -161,7 +161,8 @@ def test_filter_fallback_is_exact_and_counted():
         assert [d for d, _ in got] == [d for d, _ in want], tweak
         assert [s for _, s in got] == [s for _, s in want], tweak
         assert len(got) == {"one": 16, "two_far": 20, "none": 20}[tweak]
-        assert eng.stats()["fullsort_fallbacks"] == (0 if tweak == "none" else 1), tweak
+        # "two_far" is settled by the near-tie witness pass, only "one" needs the full sort
+        assert eng.stats()["fullsort_fallbacks"] == (1 if tweak == "one" else 0), tweak
         # PRF on, with the re-query weight at 0 so that R = 0.7 * final keeps the crafted gaps
         eng = install(idx, prf_mode="stored_rows", reranked_score_weight=0.0)
         webui_api.RERANKED_SCORE_WEIGHT = 0.0
@@ -170,6 +171,28 @@ def test_filter_fallback_is_exact_and_counted():
             P.consts["RERANKED_SCORE_WEIGHT"] = 0.0
             eng.reset_stats()
             assert_same(capture(webui_api.get_doc2vec_based_reranked_scores, f, 40), capture(P.rerank, f, 40), tweak)
-            assert eng.stats()["fullsort_fallbacks"] == (0 if tweak == "none" else 1), tweak
+            assert eng.stats()["fullsort_fallbacks"] == (1 if tweak == "one" else 0), tweak
         finally:
             webui_api.RERANKED_SCORE_WEIGHT = 0.3
+
+
+def test_clustered_top_docs_overflow_the_streaming_select():
+    """All the best docs sit in one contiguous id range: the segment-maximum threshold lets thousands of
+    survivors through, the streaming select overflows and the gated buffer select must take over."""
+    n = 100000
+    idx = synth.generate_index(n, vocab_size=300, seed=33, with_rows=True)
+    rng = np.random.default_rng(1)
+    f = rng.random(n) * 0.5
+    f[20000:26000] = 0.6 + np.linspace(0.3, 0.0, 6000)          # 6000 clustered top docs, descending with the id
+    f[77] = -np.inf
+    P = port.OraclePort(idx)
+    for mode in ("off", "stored_rows"):
+        install(idx, prf_mode=mode)
+        for topn in (100, 800):
+            if mode == "off":
+                order = np.argsort(-f, kind="stable")
+                want = port.filter_searched_result(list(zip(order.tolist(), f[order])))[:topn]
+                want = ("ok", [d for d, _ in want], [s for _, s in want])
+            else:
+                want = capture(P.rerank, f, topn)
+            assert_same(capture(webui_api.get_doc2vec_based_reranked_scores, f, topn), want, (mode, topn))
