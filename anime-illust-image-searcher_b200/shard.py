@@ -55,9 +55,10 @@ class _Dist:
         """[...] -> [world, ...]"""
         if not (self.on and self.world > 1):
             return t.unsqueeze(0)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        flat = t.contiguous().view(-1)
+        out = torch.empty((self.world * flat.numel(),), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, flat, group=self.group)       # flat: the same call shape for NCCL and gloo
+        return out.view((self.world,) + tuple(t.shape))
 
     def broadcast(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
         if self.on and self.world > 1:
