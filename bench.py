@@ -51,7 +51,8 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, text)
+        self.t_from = 0.0
 
     def start(self):
         try:
@@ -65,7 +66,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """only samples arriving after this call count (the sampler is started before the warm-up)"""
+        self.t_from = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -77,7 +82,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        for t_arr, ln in self.lines:
+            if t_arr < self.t_from:
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -151,7 +158,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--docs", type=int, default=10_000_000)
     ap.add_argument("--batch", type=int, default=16, help="queries per pass over the doc vectors (1..16)")
@@ -243,12 +250,13 @@ def main():
 
     # ---- warm-up, then the timed region ----------------------------------------------------------------
     b = args.batch
-    run_steps(args.warmup, b, 0)
-    eng.set_profiling(True)
-    eng.reset_stats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    run_steps(args.warmup, b, 0)
+    eng.set_profiling(True)
+    eng.reset_stats()
+    sampler.mark()
     dev_ms, wall_ms, h2d, d2h, n_results = run_steps(args.steps, b, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     st = eng.stats()
