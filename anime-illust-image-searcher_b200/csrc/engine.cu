@@ -158,6 +158,7 @@ struct ais_engine {
     // stats
     int64_t scan_launches = 0, kernel_launches = 0, fullsort_fallbacks = 0, bytes_device = 0;
     bool profiling = false;
+    bool use_mma = true;       // >= 5 queries per pass: tensor-core scan (3xTF32); AIS_SCAN_SIMT=1 keeps the fp32 SIMT kernel
     double scan_ms_total = 0.0;
     std::vector<cudaEvent_t> ev_pending, ev_free;
 
@@ -322,11 +323,36 @@ int launch_scan_t(ais_engine* e, const float* d_q, int nq, float* out, uint32_t*
     return AIS_OK;
 }
 
+template <int QT>
+int launch_scan_mma_t(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
+    const int64_t n_tiles = (e->n_vec + TILE_ROWS - 1) / TILE_ROWS;
+    int grid = (int)(n_tiles < e->sm_count ? n_tiles : e->sm_count);
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (e->profiling) {
+        for (cudaEvent_t* ev : {&a, &b}) {
+            if (!e->ev_free.empty()) { *ev = e->ev_free.back(); e->ev_free.pop_back(); }
+            else CK(cudaEventCreate(ev));
+        }
+        CK(cudaEventRecord(a, e->stream));
+    }
+    scan_mma_kernel<QT><<<grid, MMA_THREADS, scan_mma_smem_bytes<QT>(), e->stream>>>(e->rows.as<float>(), e->n_vec, d_q, out, e->ld,
+                                                                                    max_keys, nq);
+    LAUNCHED(e);
+    e->scan_launches++;
+    if (e->profiling) {
+        CK(cudaEventRecord(b, e->stream));
+        e->ev_pending.push_back(a);
+        e->ev_pending.push_back(b);
+    }
+    return AIS_OK;
+}
+
 int launch_scan(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
     if (e->n_vec == 0) return AIS_OK;
     if (nq <= 1) return launch_scan_t<1>(e, d_q, nq, out, max_keys);
     if (nq <= 2) return launch_scan_t<2>(e, d_q, nq, out, max_keys);
     if (nq <= 4) return launch_scan_t<4>(e, d_q, nq, out, max_keys);
+    if (e->use_mma) return nq <= 8 ? launch_scan_mma_t<8>(e, d_q, nq, out, max_keys) : launch_scan_mma_t<16>(e, d_q, nq, out, max_keys);
     if (nq <= 8) return launch_scan_t<8>(e, d_q, nq, out, max_keys);
     return launch_scan_t<16>(e, d_q, nq, out, max_keys);
 }
@@ -337,6 +363,8 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<4>()));
     CK(cudaFuncSetAttribute(scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<8>()));
     CK(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<16>()));
+    CK(cudaFuncSetAttribute(scan_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<8>()));
+    CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
     return AIS_OK;
 }
@@ -884,6 +912,8 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
     cudaError_t se = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
     if (se != cudaSuccess) { delete e; return fail(AIS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
     e->stream = e->own_stream;
+    const char* simt = getenv("AIS_SCAN_SIMT");
+    e->use_mma = !(simt && simt[0] == '1');
     int s = set_scan_attrs();
     if (s != AIS_OK) { cudaStreamDestroy(e->own_stream); delete e; return s; }
     *out = e;

@@ -95,6 +95,9 @@ def test_fresh_index_vs_oracle(n_docs, vocab, tf_frac):
 
 
 def test_batched_queries_equal_single_queries():
+    """<= 4 queries per pass run the same fp32 SIMT scan (bit-equal results for any batching); >= 5 queries per
+    pass run the tensor-core scan (3xTF32, fp32-level accuracy): same ranking within the score tolerance."""
+    from gpu_util import same_ranking
     idx = synth.generate_index(40000, vocab_size=2000, seed=77)
     queries = synth.generate_queries(idx, 37, seed=3)
     t2i = idx.token2id
@@ -102,14 +105,43 @@ def test_batched_queries_equal_single_queries():
     qs = [Q.make_query(q, t2i, infer) for q in queries]
     single = E.SearchEngine.from_index(idx, max_batch=1)
     ref = single.search_raw(qs, 100, E.PRF_STORED_ROWS)
-    for mb in (2, 3, 8, 16):
+    for mb in (2, 3, 4, 8, 13, 16):
         eng = E.SearchEngine.from_index(idx, max_batch=mb)
         got = eng.search_raw(qs, 100, E.PRF_STORED_ROWS)
-        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+        assert np.array_equal(got[3], ref[3])
         for q in range(len(qs)):
             c = ref[2][q]
-            assert np.array_equal(got[0][q, :c], ref[0][q, :c]), (mb, q)
-            assert np.array_equal(got[1][q, :c], ref[1][q, :c]), (mb, q)      # same kernels, same order: bit-equal
+            if mb <= 4:
+                assert got[2][q] == c
+                assert np.array_equal(got[0][q, :c], ref[0][q, :c]), (mb, q)
+                assert np.array_equal(got[1][q, :c], ref[1][q, :c]), (mb, q)      # same kernels, same order: bit-equal
+            elif got[2][q] == c:
+                msg = same_ranking(got[0][q, :c].tolist(), got[1][q, :c].tolist(), ref[0][q, :c].tolist(), ref[1][q, :c].tolist())
+                assert msg is None, (mb, q, msg)
+            else:       # a near-threshold gap of filter_searched_result fell on the other side (see gpu_util)
+                m = min(c, got[2][q])
+                assert same_ranking(got[0][q, :m].tolist(), got[1][q, :m].tolist(), ref[0][q, :m].tolist(), ref[1][q, :m].tolist()) is None
+        eng.close()
+
+
+def test_tensor_core_scan_accuracy():
+    """index[vec] through the batched (mma.sync 3xTF32) scan against the fp64 dot product: fp32-level error."""
+    idx = synth.generate_index(20000, vocab_size=500, seed=12)
+    rng = np.random.default_rng(4)
+    for mb in (8, 16):
+        eng = E.SearchEngine.from_index(idx, max_batch=mb)
+        vecs = rng.standard_normal((mb, 300)).astype(np.float32)
+        vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+        qs = [E.Query(v, np.array([0], np.int32), np.array([1.0])) for v in vecs]
+        # stage_score leaves the dense scores in the engine; read them back through the combined-score seam
+        import torch
+        maxes = torch.empty((mb, 2), dtype=torch.float64, device="cuda")
+        eng.stage_score(qs, maxes)
+        torch.cuda.synchronize()
+        eng.synchronize()
+        want_max = (idx.rows.astype(np.float64) @ vecs.T.astype(np.float64)).max(axis=0)
+        got_max = maxes.cpu().numpy()[:, 1]
+        assert np.abs(got_max - want_max).max() <= 2e-6 * np.abs(want_max).max()
         eng.close()
 
 
