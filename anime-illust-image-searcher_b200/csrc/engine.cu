@@ -144,6 +144,7 @@ struct ais_engine {
     Buf blk_keys, blk_ids, grp_keys, grp_ids, cand_keys, cand_ids, rest_keys, rest_ids, rest_count;
     Buf out_ids, out_scores, out_count, out_amb;
     Buf fs_keys, fs_ids, fs_count;
+    Buf bm25_slices;
     Buf seg_max, sel_thr, surv_count, surv_keys, surv_ids, gate, witness, last_keys, wit_table;
     uint64_t* h_last_keys = nullptr;
     int sel_k_cap = 0, out_topn_cap = 0;
@@ -347,14 +348,23 @@ int launch_scan_mma_t(ais_engine* e, const float* d_q, int nq, float* out, uint3
     return AIS_OK;
 }
 
-int launch_scan(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
-    if (e->n_vec == 0) return AIS_OK;
+int launch_scan_one(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
     if (nq <= 1) return launch_scan_t<1>(e, d_q, nq, out, max_keys);
     if (nq <= 2) return launch_scan_t<2>(e, d_q, nq, out, max_keys);
     if (nq <= 4) return launch_scan_t<4>(e, d_q, nq, out, max_keys);
     if (e->use_mma) return nq <= 8 ? launch_scan_mma_t<8>(e, d_q, nq, out, max_keys) : launch_scan_mma_t<16>(e, d_q, nq, out, max_keys);
     if (nq <= 8) return launch_scan_t<8>(e, d_q, nq, out, max_keys);
     return launch_scan_t<16>(e, d_q, nq, out, max_keys);
+}
+
+// one pass over the rows per MAX_QT queries (the query buffer is zero-padded to a power of two >= nq)
+int launch_scan(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
+    if (e->n_vec == 0) return AIS_OK;
+    for (int q0 = 0; q0 < nq; q0 += MAX_QT) {
+        const int m = nq - q0 < MAX_QT ? nq - q0 : MAX_QT;
+        TRY(launch_scan_one(e, d_q + (size_t)q0 * DIM, m, out + (size_t)q0 * e->ld, max_keys + q0));
+    }
+    return AIS_OK;
 }
 
 int set_scan_attrs() {
@@ -365,6 +375,7 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<8>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
+    CK(cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
     return AIS_OK;
 }
@@ -395,9 +406,17 @@ int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bo
 
 int launch_bm25(ais_engine* e, int nq) {
     if (e->n_bm25 <= 0) return AIS_OK;
-    dim3 grid((unsigned)((e->n_bm25 + BM25_TILE - 1) / BM25_TILE), (unsigned)nq);
-    bm25_kernel<<<grid, BM25_THREADS, 0, e->stream>>>(
-        e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->has_tf ? e->post_tf.as<int32_t>() : nullptr,
+    const int64_t n_tiles = (e->n_bm25 + BM25_TILE - 1) / BM25_TILE;
+    int t_cap = 1;
+    for (int q = 0; q < nq; ++q) t_cap = e->h_qt[q].n_terms > t_cap ? e->h_qt[q].n_terms : t_cap;
+    TRY(dev_alloc(e, e->bm25_slices, (size_t)e->qt_cap * t_cap * (n_tiles + 1) * sizeof(int64_t)));
+    bm25_slices_kernel<<<dim3((unsigned)((n_tiles + 1 + 127) / 128), (unsigned)(nq * t_cap)), 128, 0, e->stream>>>(
+        e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->n_vocab, e->d_qt.as<QueryTerms>(), t_cap, n_tiles,
+        e->bm25_slices.as<int64_t>());
+    LAUNCHED(e);
+    dim3 grid((unsigned)n_tiles, (unsigned)nq);
+    bm25_kernel<<<grid, BM25_THREADS, BM25_SMEM, e->stream>>>(
+        e->bm25_slices.as<int64_t>(), t_cap, n_tiles, e->post_doc.as<int32_t>(), e->has_tf ? e->post_tf.as<int32_t>() : nullptr,
         e->idf.as<double>(), e->kd.as<double>(), e->n_bm25, e->n_vocab, e->d_qt.as<QueryTerms>(), e->p.require_magic,
         e->p.k1 + 1.0, e->bm25.as<double>(), e->ld, e->maxb_key.as<uint64_t>());
     LAUNCHED(e);
@@ -499,12 +518,12 @@ int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
     TRY(ensure_work(e));
     if (nq < 1 || nq > e->p.max_batch) return fail(AIS_ERR_INVALID, "nq %d outside [1, max_batch=%d]", nq, e->p.max_batch);
     TRY(upload_queries(e, qs, nq, true, true));
-    init_keys_kernel<<<1, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
+    init_keys_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
                                              e->maxr_key.as<uint64_t>(), e->status.as<int32_t>(), nq, 1);
     LAUNCHED(e);
     TRY(launch_bm25(e, nq));
     TRY(launch_scan(e, e->d_q.as<float>(), nq, e->sim.as<float>(), e->maxs_key.as<uint32_t>()));
-    maxes_kernel<<<1, 64, 0, e->stream>>>(e->maxb_key.as<uint64_t>(), e->maxs_key.as<uint32_t>(), nq, d_maxes);
+    maxes_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxb_key.as<uint64_t>(), e->maxs_key.as<uint32_t>(), nq, d_maxes);
     LAUNCHED(e);
     e->cur_nq = nq;
     e->cur_prf = false;
@@ -577,12 +596,12 @@ int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows,
                                                    e->status.as<int32_t>());
         LAUNCHED(e);
     }
-    init_keys_kernel<<<1, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
+    init_keys_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
                                              e->maxr_key.as<uint64_t>(), e->status.as<int32_t>(), nq, 2);
     LAUNCHED(e);
     TRY(launch_scan(e, e->d_q2.as<float>(), nq, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
     TRY(do_requery_select(e, nq, k, d_keys, d_ids));
-    maxr_kernel<<<1, 64, 0, e->stream>>>(e->maxr_key.as<uint64_t>(), nq, d_max_r);
+    maxr_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxr_key.as<uint64_t>(), nq, d_max_r);
     LAUNCHED(e);
     e->cur_prf = true;
     return AIS_OK;
@@ -884,7 +903,7 @@ void ais_default_params(ais_params* p) {
 
 static int validate_params(const ais_params* p) {
     if (p->prf_depth < 1 || p->prf_depth > MAX_DEPTH) return fail(AIS_ERR_INVALID, "prf_depth %d outside [1, %d]", p->prf_depth, MAX_DEPTH);
-    if (p->max_batch < 1 || p->max_batch > MAX_QT) return fail(AIS_ERR_INVALID, "max_batch %d outside [1, %d]", p->max_batch, MAX_QT);
+    if (p->max_batch < 1 || p->max_batch > MAX_BATCH) return fail(AIS_ERR_INVALID, "max_batch %d outside [1, %d]", p->max_batch, MAX_BATCH);
     return AIS_OK;
 }
 
@@ -929,7 +948,7 @@ int ais_destroy(ais_engine* e) {
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
                    &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->sel_thr, &e->surv_count,
-                   &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table})
+                   &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,
                     (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small, (void*)e->h_last_keys})

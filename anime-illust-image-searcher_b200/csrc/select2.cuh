@@ -30,15 +30,17 @@ constexpr int COLLECT_THREADS = 256;
 struct ScoreCombine {      // pass 1: webui.py:376-383, also stores the combined score
     const float* sim; const double* bm25; double* fin; float maxs; double maxb; CombineParams cp;
     __device__ __forceinline__ bool operator()(int64_t i, int64_t, uint64_t& key) const {
-        float s = sim[i];
-        double b = bm25[i];
+        float s = __ldcs(sim + i);          // read once: streaming loads / stores keep L2 for the posting lists
+        double b = __ldcs(bm25 + i);
         if (maxs > 0.0f) s = __fdiv_rn(s, maxs);
-        if (maxb > 0.0) b = __ddiv_rn(b, maxb);
+        // 0 / max = 0 and -inf / max = -inf exactly: only docs with a BM25 contribution pay for the fp64 division
+        if (maxb > 0.0 && b != 0.0 && b != -INFINITY) b = __ddiv_rn(b, maxb);
         const double f = __dadd_rn(__dmul_rn(cp.wb, b), (double)__fmul_rn(cp.wd, s));
-        fin[i] = f;
+        __stcs(fin + i, f);
         key = dkey(f);
         return true;
     }
+    __device__ __forceinline__ bool is_seed(int64_t) const { return false; }
 };
 struct ScoreFinal {        // stored combined scores
     const double* fin;
@@ -46,15 +48,19 @@ struct ScoreFinal {        // stored combined scores
         key = dkey(fin[i]);
         return true;
     }
+    __device__ __forceinline__ bool is_seed(int64_t) const { return false; }
 };
 struct ScoreRerank {       // pass 2: webui.py:208 blend; the PRF seeds are not candidates (webui.py:217)
     const double* fin; const float* rer; CombineParams cp; const int64_t* seeds; int depth;
     __device__ __forceinline__ bool operator()(int64_t i, int64_t id, uint64_t& key) const {
         const double r = __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)__fmul_rn(cp.wr, rer[i]));
         key = dkey(r);
-        bool keep = true;
-        for (int t = 0; t < depth; ++t) keep = keep && (seeds[t] != id);
-        return keep;
+        return true;                 // seeds are filtered by is_seed() only for docs that would otherwise qualify
+    }
+    __device__ __forceinline__ bool is_seed(int64_t id) const {
+        bool hit = false;
+        for (int t = 0; t < depth; ++t) hit = hit || (seeds[t] == id);
+        return hit;
     }
 };
 
@@ -112,23 +118,25 @@ segmax_kernel(SelectArgs a) {
 #pragma unroll 1
             for (; i + 96 < hi; i += 128) {
                 uint64_t k0, k1, k2, k3;
-                const bool o0 = f(i, a.id_base + i, k0);
-                const bool o1 = f(i + 32, a.id_base + i + 32, k1);
-                const bool o2 = f(i + 64, a.id_base + i + 64, k2);
-                const bool o3 = f(i + 96, a.id_base + i + 96, k3);
-                uint64_t m01 = k0 > k1 ? k0 : k1, m23 = k2 > k3 ? k2 : k3;
-                uint64_t m = m01 > m23 ? m01 : m23;
+                f(i, a.id_base + i, k0);
+                f(i + 32, a.id_base + i + 32, k1);
+                f(i + 64, a.id_base + i + 64, k2);
+                f(i + 96, a.id_base + i + 96, k3);
+                const uint64_t m01 = k0 > k1 ? k0 : k1, m23 = k2 > k3 ? k2 : k3;
+                const uint64_t m = m01 > m23 ? m01 : m23;
                 all_best = m > all_best ? m : all_best;
-                k0 = o0 ? k0 : KEY_EMPTY; k1 = o1 ? k1 : KEY_EMPTY; k2 = o2 ? k2 : KEY_EMPTY; k3 = o3 ? k3 : KEY_EMPTY;
-                m01 = k0 > k1 ? k0 : k1; m23 = k2 > k3 ? k2 : k3;
-                m = m01 > m23 ? m01 : m23;
-                best = m > best ? m : best;
+                if (m > best) {                       // rare after the first few iterations
+                    if (k0 > best && !f.is_seed(a.id_base + i)) best = k0;
+                    if (k1 > best && !f.is_seed(a.id_base + i + 32)) best = k1;
+                    if (k2 > best && !f.is_seed(a.id_base + i + 64)) best = k2;
+                    if (k3 > best && !f.is_seed(a.id_base + i + 96)) best = k3;
+                }
             }
             for (; i < hi; i += 32) {
                 uint64_t k;
-                const bool ok = f(i, a.id_base + i, k);
+                f(i, a.id_base + i, k);
                 all_best = k > all_best ? k : all_best;
-                if (ok) best = k > best ? k : best;
+                if (k > best && !f.is_seed(a.id_base + i)) best = k;
             }
         });
         best = warp_max_u64(best);
@@ -193,19 +201,33 @@ collect_kernel(SelectArgs a) {
     const int64_t stride = (int64_t)gridDim.x * COLLECT_THREADS;
     const int64_t n_round = ((a.n + 31) / 32) * 32;          // whole warps stay together for the ballots
     with_functor<(MODE == 0 ? 1 : MODE)>(a, qi, seeds, [&](auto& f) {   // pass 1 re-reads the stored finals
-        for (int64_t i = (int64_t)blockIdx.x * COLLECT_THREADS + threadIdx.x; i < n_round; i += stride) {
-            uint64_t key = KEY_EMPTY;
-            bool pass = false;
-            if (i < a.n) pass = f(i, a.id_base + i, key) && key >= T;
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(cnt, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (pass) {
-                    const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (pos < SURV_CAP) { sk[pos] = key; si[pos] = a.id_base + i; }
+        for (int64_t i0 = (int64_t)blockIdx.x * COLLECT_THREADS + threadIdx.x; i0 < n_round; i0 += 4 * stride) {
+            uint64_t key[4];
+            bool pass[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                         // four independent loads in flight per thread
+                const int64_t i = i0 + u * stride;
+                key[u] = KEY_EMPTY;
+                if (i < a.n) f(i, a.id_base + i, key[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * stride;
+                pass[u] = i < a.n && key[u] >= T && !f.is_seed(a.id_base + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u * stride >= n_round) break;            // warp-uniform
+                const unsigned m = __ballot_sync(0xffffffffu, pass[u]);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(cnt, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (pass[u]) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < SURV_CAP) { sk[pos] = key[u]; si[pos] = a.id_base + i0 + u * stride; }
+                    }
                 }
             }
         }

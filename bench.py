@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--docs", type=int, default=10_000_000)
-    ap.add_argument("--batch", type=int, default=16, help="queries per pass over the doc vectors (1..16)")
+    ap.add_argument("--batch", type=int, default=16, help="queries per engine batch (1..128); every 16 share one pass over the doc vectors")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-docs", type=int, default=100_000)
     ap.add_argument("--cpu-queries", type=int, default=12)
@@ -193,7 +193,7 @@ def main():
     # ---- stage the shard [lo, hi) of the synthetic index into HBM -----------------------------------
     t_build = time.perf_counter()
     lo, hi = shard.shard_bounds(args.docs, world, rank)
-    eng = E.SearchEngine(device=local_rank, max_batch=args.batch)
+    eng = E.SearchEngine(device=local_rank, max_batch=max(args.batch, 64) if args.sweep else args.batch)
     rows = eng.rows_tensor(hi - lo)
     sh = synth_torch.generate_shard(lo, hi, rows, vocab=VOCAB, seed=SEED)
     idf, avgdl, df = synth_torch.global_stats(sh, args.docs)
@@ -231,12 +231,15 @@ def main():
         ev0.record()
         h2d = d2h = 0
         n_results = 0
+        checksum = 0
         for s in range(n_steps):
             qs = batch_at(first_step + s, b)
             ids, scores, counts, status, _ = search(qs)
             h2d += sum(q.vec.nbytes + q.term_ids.nbytes + q.weights.nbytes for q in qs)
             d2h += ids.nbytes + scores.nbytes + counts.nbytes + status.nbytes
             n_results += int(counts.sum())
+            for j in range(len(qs)):
+                checksum = (checksum * 1000003 + int(ids[j, :counts[j]].sum()) + 7 * int(counts[j])) % (1 << 61)
         ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -246,7 +249,7 @@ def main():
         t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), h2d // max(n_steps, 1), d2h // max(n_steps, 1), n_results
+        return float(t[0]), float(t[1]), h2d // max(n_steps, 1), d2h // max(n_steps, 1), n_results, checksum
 
     # ---- warm-up, then the timed region ----------------------------------------------------------------
     b = args.batch
@@ -257,7 +260,7 @@ def main():
     eng.set_profiling(True)
     eng.reset_stats()
     sampler.mark()
-    dev_ms, wall_ms, h2d, d2h, n_results = run_steps(args.steps, b, args.warmup)
+    dev_ms, wall_ms, h2d, d2h, n_results, checksum = run_steps(args.steps, b, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     st = eng.stats()
     eng.set_profiling(False)
@@ -280,12 +283,10 @@ def main():
     sweep = None
     if args.sweep:
         sweep = {}
-        for bb in (1, 2, 4, 8, 16):
-            if bb > args.batch:
-                break
+        for bb in (1, 2, 4, 8, 16, 32, 64):
             run_steps(2, bb, 0)
             eng.set_profiling(True); eng.reset_stats()
-            ms, wms, _, _, _ = run_steps(max(4, args.steps // 2), bb, 2)
+            ms, wms, _, _, _, _ = run_steps(max(4, args.steps // 2), bb, 2)
             s2 = eng.stats(); eng.set_profiling(False)
             k = max(4, args.steps // 2)
             sm = s2["scan_ms_total"] / max(1, s2["scan_launches"])
@@ -321,6 +322,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
             "results_per_step": n_results / args.steps,
+            "results_checksum": checksum,      # same queries -> same value for every --gpus N (doc ids of all results)
             "fullsort_fallbacks": int(st["fullsort_fallbacks"]) + (S.fullsort_fallbacks if S is not None else 0),
             "index_build_s": t_build,
         }

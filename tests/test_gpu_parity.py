@@ -105,7 +105,7 @@ def test_batched_queries_equal_single_queries():
     qs = [Q.make_query(q, t2i, infer) for q in queries]
     single = E.SearchEngine.from_index(idx, max_batch=1)
     ref = single.search_raw(qs, 100, E.PRF_STORED_ROWS)
-    for mb in (2, 3, 4, 8, 13, 16):
+    for mb in (2, 3, 4, 8, 13, 16, 37):
         eng = E.SearchEngine.from_index(idx, max_batch=mb)
         got = eng.search_raw(qs, 100, E.PRF_STORED_ROWS)
         assert np.array_equal(got[3], ref[3])
