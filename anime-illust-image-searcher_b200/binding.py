@@ -80,6 +80,7 @@ SIGNATURES = {
     "ais_stage_sort_finish": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "ais_max_select_k": (C.c_int, []),
     "ais_sort_capacity": (_i64, [_i64]),
+    "ais_debug_read": (C.c_int, [_vp, _i32, _i32, _vp]),
     "ais_set_profiling": (C.c_int, [_vp, C.c_int]),
     "ais_get_stats": (C.c_int, [_vp, C.POINTER(AisStats)]),
     "ais_reset_stats": (C.c_int, [_vp]),

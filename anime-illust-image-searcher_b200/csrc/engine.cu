@@ -1265,6 +1265,20 @@ int ais_stage_sort_finish(ais_engine* e, int32_t query, uint64_t* d_keys, int64_
     return do_sort_finish(e, query, d_keys, d_ids, n_entries, d_max_r, topn, out_ids, out_scores, out_count, out_status);
 }
 
+// test seam: read back a per-doc work array of the current batch (which: 0 sim fp32, 1 bm25 fp64, 2 combined fp64, 3 rer fp32)
+int ais_debug_read(ais_engine* e, int32_t which, int32_t query, void* out) {
+    if (!e || !out || query < 0 || query >= e->qt_cap || which < 0 || which > 3) return fail(AIS_ERR_INVALID, "bad argument");
+    DeviceGuard g(e->device);
+    const size_t n = (size_t)e->n();
+    const void* src = which == 0 ? (const void*)(e->sim.as<float>() + (size_t)query * e->ld)
+                    : which == 1 ? (const void*)(e->bm25.as<double>() + (size_t)query * e->ld)
+                    : which == 2 ? (const void*)(e->fin.as<double>() + (size_t)query * e->ld)
+                                 : (const void*)(e->rer.as<float>() + (size_t)query * e->ld);
+    CK(cudaMemcpyAsync(out, src, n * ((which == 0 || which == 3) ? 4 : 8), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return AIS_OK;
+}
+
 // ---- introspection ----------------------------------------------------------------------------------------
 int ais_set_profiling(ais_engine* e, int on) {
     if (!e) return fail(AIS_ERR_INVALID, "NULL engine");

@@ -366,6 +366,13 @@ class SearchEngine:
                                         _ptr(out_scores), C.byref(cnt), C.byref(st)))
         return out_ids, out_scores, cnt.value, st.value
 
+    def debug_read(self, which: str, query: int) -> np.ndarray:
+        """Per-doc work array of the current batch: 'sim' | 'bm25' | 'fin' | 'rer' (test seam)."""
+        code = {"sim": 0, "bm25": 1, "fin": 2, "rer": 3}[which]
+        out = np.empty(self.n_docs, dtype=np.float32 if code in (0, 3) else np.float64)
+        check(lib.ais_debug_read(self._h, code, query, _ptr(out)))
+        return out
+
     # ---- introspection -----------------------------------------------------------------------------
     def set_profiling(self, on: bool) -> None:
         check(lib.ais_set_profiling(self._h, 1 if on else 0))

@@ -39,7 +39,7 @@ def embedding_table(vocab: int, seed: int, device) -> torch.Tensor:
 
 def generate_shard(lo: int, hi: int, rows_out: torch.Tensor, vocab: int = DEFAULT_VOCAB, seed: int = 20260101,
                    mean_tags: float = 28.0, sigma: float = 0.45, min_tags: int = 3, max_tags: int = 120,
-                   width: int = 192) -> TorchShard:
+                   width: int = 192, chunk: int = CHUNK) -> TorchShard:
     """Fill rows_out [hi-lo, 300] (device) and return the shard's posting lists."""
     device = rows_out.device
     n = hi - lo
@@ -50,12 +50,12 @@ def generate_shard(lo: int, hi: int, rows_out: torch.Tensor, vocab: int = DEFAUL
     E = embedding_table(vocab, seed, device)
     keys: List[torch.Tensor] = []
     lens: List[torch.Tensor] = []
-    c0 = lo // CHUNK
-    c1 = (hi + CHUNK - 1) // CHUNK if n > 0 else c0
+    c0 = lo // chunk
+    c1 = (hi + chunk - 1) // chunk if n > 0 else c0
     for c in range(c0, c1):
         g = torch.Generator(device=device)
         g.manual_seed(seed * 1000003 + c)
-        m = CHUNK
+        m = chunk
         want = torch.exp(math.log(mean_tags) + sigma * torch.randn((m,), generator=g, device=device))
         want = want.round().clamp_(min_tags, max_tags).to(torch.int64)
         draws = torch.searchsorted(cdf, torch.rand((m, width), generator=g, device=device)).clamp_(max=vocab - 1)
@@ -71,15 +71,21 @@ def generate_shard(lo: int, hi: int, rows_out: torch.Tensor, vocab: int = DEFAUL
         rank = torch.cumsum(first, dim=1)
         keep = first & (rank <= want[:, None])
         # restrict the chunk to the docs of this shard
-        d0 = c * CHUNK
-        a, b = max(lo, d0) - d0, min(hi, d0 + CHUNK) - d0
+        d0 = c * chunk
+        a, b = max(lo, d0) - d0, min(hi, d0 + chunk) - d0
         keep, draws, noise, scale = keep[a:b], draws[a:b], noise[a:b], scale[a:b]
         cnt = keep.sum(dim=1)
         r_idx, c_idx = torch.nonzero(keep, as_tuple=True)                  # row-major: draw order inside a doc
         tags = draws[r_idx, c_idx]
-        # stored row = s * (mean E[tags] + 0.3 * noise)
+        # stored row = s * (mean E[tags] + 0.3 * noise); the sum runs over the tag positions in draw order so that
+        # it is bit-reproducible (index_add_ on CUDA uses atomics, i.e. an arbitrary summation order)
+        width_out = int(cnt.max().item()) if cnt.numel() else 0
+        padded = torch.zeros((b - a, max(width_out, 1)), dtype=torch.int64, device=device)
+        padded[r_idx, rank[a:b][r_idx, c_idx] - 1] = tags
         acc = torch.zeros((b - a, DIM), device=device, dtype=torch.float32)
-        acc.index_add_(0, r_idx, E[tags])
+        for kpos in range(width_out):
+            live = (cnt > kpos).to(torch.float32)[:, None]
+            acc += E[padded[:, kpos]] * live
         acc /= cnt.clamp(min=1).to(torch.float32)[:, None]
         local0 = d0 + a - lo
         rows_out[local0: local0 + (b - a)] = scale * (acc + 0.3 * noise)

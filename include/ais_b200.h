@@ -220,6 +220,10 @@ int ais_stage_sort_finish(ais_engine* e, int32_t query, uint64_t* d_keys, int64_
                           const double* d_max_r /* NULL: no-PRF branch */, int32_t topn, int64_t* out_ids,
                           double* out_scores, int32_t* out_count, int32_t* out_status);
 
+/* test seam: per-doc work array of the current batch (which: 0 dot fp32, 1 bm25 fp64, 2 combined fp64,
+ * 3 re-query dot fp32) for one query of the batch -> host array [n_local]. */
+int ais_debug_read(ais_engine* e, int32_t which, int32_t query, void* out);
+
 /* --- introspection ----------------------------------------------------------------------- */
 int ais_set_profiling(ais_engine* e, int on);   /* CUDA-event timing of every scan launch */
 int ais_get_stats(ais_engine* e, ais_stats* out);

@@ -9,12 +9,12 @@ from ais_b200 import shard, synth_torch
 
 def _gen(lo, hi, vocab=500):
     rows = torch.zeros((hi - lo, 300), dtype=torch.float32)
-    sh = synth_torch.generate_shard(lo, hi, rows, vocab=vocab, seed=11)
+    sh = synth_torch.generate_shard(lo, hi, rows, vocab=vocab, seed=11, chunk=8192)
     return rows, sh
 
 
 def test_shards_add_up_to_the_same_corpus():
-    n = synth_torch.CHUNK + 7000
+    n = 2 * 8192 + 3000
     rows1, one = _gen(0, n)
     parts = [_gen(*shard.shard_bounds(n, 3, r)) for r in range(3)]
     assert torch.equal(torch.cat([p[0] for p in parts]), rows1)
