@@ -15,9 +15,12 @@
 
 namespace ais {
 
-constexpr int BM25_TILE = 8192;                  // docs per block: fewer, fatter blocks amortise the per-term barriers
-constexpr int BM25_THREADS = 512;
-constexpr int BM25_SMEM = BM25_TILE * (8 + 1 + 1);   // fp64 accumulators + exclude flags + required-term counters
+constexpr int BM25_SUB = 256;                    // docs per warp-private sub-tile
+constexpr int BM25_WARPS = 8;                    // warps (= consecutive sub-tiles of one query) per block
+constexpr int BM25_THREADS = 32 * BM25_WARPS;
+constexpr int BM25_STAGE = 256;                  // staged postings per (sub-tile, query); denser slices take the direct path
+constexpr int BM25_WARP_SMEM = BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8 + 4 * BM25_SUB;
+constexpr int BM25_SMEM = BM25_WARPS * BM25_WARP_SMEM;
 
 struct QueryTerms {  // device-resident, one per query of the pass
     int32_t n_terms;
@@ -34,109 +37,252 @@ __global__ void kd_kernel(const int64_t* __restrict__ doc_len, int64_t n, double
     kd[i] = __dmul_rn(k1, __dadd_rn(one_minus_b, __dmul_rn(b, r)));
 }
 
-// slices[(q * t_cap + j) * (n_tiles + 1) + tile] = first posting of query q's j-th term whose doc id is
-// >= tile * BM25_TILE.  One thread per entry: the binary searches are independent, so their latency is
-// hidden by parallelism instead of being paid serially at the head of every bm25 block.
+// slices[(q * t_cap + j) * (n_sub + 1) + sub] = first posting of query q's j-th term whose doc id is
+// >= sub * BM25_SUB (absolute index into post_doc).  One thread per entry: the binary searches are
+// independent, so their latency is hidden by parallelism instead of being paid serially in the scoring kernel.
 __global__ void bm25_slices_kernel(const int64_t* __restrict__ post_ptr, const int32_t* __restrict__ post_doc, int32_t n_vocab,
-                                   const QueryTerms* __restrict__ queries, int t_cap, int64_t n_tiles,
+                                   const QueryTerms* __restrict__ queries, int t_cap, int64_t n_sub,
                                    int64_t* __restrict__ slices) {
-    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t sub = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int qi = blockIdx.y / t_cap, j = blockIdx.y - qi * t_cap;
-    if (tile > n_tiles || j >= queries[qi].n_terms) return;
+    if (sub > n_sub || j >= queries[qi].n_terms) return;
     const int t = queries[qi].term[j];
     int64_t a = 0, b = 0;
     if (t >= 0 && t < n_vocab) { a = post_ptr[t]; b = post_ptr[t + 1]; }
-    const int64_t target = tile * BM25_TILE;
+    const int64_t target = sub * BM25_SUB;
     while (a < b) {
         const int64_t m = (a + b) >> 1;
         if ((int64_t)post_doc[m] < target) a = m + 1; else b = m;
     }
-    slices[((int64_t)qi * t_cap + j) * (n_tiles + 1) + tile] = a;
+    slices[((int64_t)qi * t_cap + j) * (n_sub + 1) + sub] = a;
 }
 
+struct Bm25Args {
+    const int64_t* slices; int t_cap; int64_t n_sub;
+    const int32_t* post_doc; const int32_t* post_tf;          // post_tf may be null: tf == 1
+    const double* idf; const double* kd; int64_t n; int32_t n_vocab;
+    const QueryTerms* queries; double magic, k1p1;
+    // phase 0: per-query maximum (+ optional dense scores for the compute_bm25_scores seam)
+    uint64_t* max_keys; double* dense_out; int64_t ld;
+    // phase 1: normalise + combine with the dot scores (webui.py:376-383), store the combined scores, segment maxima
+    const float* sim; double* fin; const double* maxes; double wb; float wd;
+    uint64_t* seg_max; int seg_mod;                            // seg_max[q][sub % seg_mod]
+};
+
+// One WARP per (sub-tile of BM25_SUB docs, query), no block barriers: every warp runs its own dependency chain
+// (slice bounds -> postings -> K_d -> fp64 contribution -> ordered accumulation -> epilogue), so an SM overlaps
+// ~40 of them.  The postings of ALL the query's terms that fall into the sub-tile are first staged in the warp's
+// shared memory with their contributions (independent global loads), then summed term by term, in the query's
+// term order (fp64 addition is not associative; webui.py:139-170 adds term by term), out of shared memory only.
+template <int PHASE>
 __global__ void __launch_bounds__(BM25_THREADS)
-bm25_kernel(const int64_t* __restrict__ slices, int t_cap, int64_t n_tiles, const int32_t* __restrict__ post_doc,
-            const int32_t* __restrict__ post_tf,  // may be null: tf == 1
-            const double* __restrict__ idf, const double* __restrict__ kd, int64_t n, int32_t n_vocab,
-            const QueryTerms* __restrict__ queries, double magic, double k1p1,
-            double* __restrict__ out, int64_t ld,       // [nq][ld]
-            uint64_t* __restrict__ max_keys) {          // [nq] dkey images
+bm25_warp_kernel(Bm25Args A) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
-    double* acc = reinterpret_cast<double*>(bm25_smem);
-    uint8_t* excl = bm25_smem + (size_t)BM25_TILE * 8;
-    uint8_t* reqc = excl + BM25_TILE;
-    __shared__ uint64_t wmax[BM25_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t sub = (int64_t)blockIdx.x * BM25_WARPS + warp;
+    if (sub >= A.n_sub) return;
+    unsigned char* base = bm25_smem + (size_t)warp * BM25_WARP_SMEM;
+    double* acc = reinterpret_cast<double*>(base);
+    double* st_val = reinterpret_cast<double*>(base + BM25_SUB * 8);
+    int* off = reinterpret_cast<int*>(base + BM25_SUB * 8 + BM25_STAGE * 8);                 // [MAX_TERMS + 1]
+    int64_t* sl_a = reinterpret_cast<int64_t*>(base + BM25_SUB * 8 + BM25_STAGE * 8 + 264);  // [MAX_TERMS]
+    uint8_t* excl = base + BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8;
+    uint8_t* reqc = excl + BM25_SUB;
+    uint8_t* st_doc = reqc + BM25_SUB;
+    uint8_t* need = st_doc + BM25_SUB;
 
     const int qi = blockIdx.y;
-    const QueryTerms& Q = queries[qi];
+    const QueryTerms& Q = A.queries[qi];
     const int T = Q.n_terms;
-    const int tid = threadIdx.x;
-    const int64_t lo = (int64_t)blockIdx.x * BM25_TILE;
-    const int64_t hi = (lo + BM25_TILE < n) ? lo + BM25_TILE : n;
-    const int64_t* sl = slices + (int64_t)qi * t_cap * (n_tiles + 1) + blockIdx.x;
+    const int64_t lo = sub * BM25_SUB;
+    const int64_t hi = (lo + BM25_SUB < A.n) ? lo + BM25_SUB : A.n;
+    const int64_t* sl = A.slices + (int64_t)qi * A.t_cap * (A.n_sub + 1) + sub;
 
-    // does any term of the query touch this tile at all?  (most tiles of most queries: no)
-    bool touched = false;
-    for (int j = 0; j < T; ++j) touched = touched || (sl[(int64_t)j * (n_tiles + 1)] != sl[(int64_t)j * (n_tiles + 1) + 1]);
-    int n_required = 0;
-    if (touched) {
-        for (int i = tid; i < BM25_TILE; i += BM25_THREADS) {
-            acc[i] = 0.0;
-            excl[i] = 0;
-            reqc[i] = 0;
+    // slice bounds of every term, exclusive prefix sum of their lengths, number of required terms
+    int n_required = 0, carry = 0;
+    for (int j0 = 0; j0 < T; j0 += 32) {
+        const int j = j0 + lane;
+        int len = 0;
+        bool req = false;
+        if (j < T) {
+            const int64_t a = sl[(int64_t)j * (A.n_sub + 1)], b = sl[(int64_t)j * (A.n_sub + 1) + 1];
+            sl_a[j] = a;
+            len = (int)(b - a);
+            req = Q.weight[j] > A.magic;                 // webui.py:161 (1000 itself is NOT required)
         }
-        __syncthreads();
+        n_required += __popc(__ballot_sync(0xffffffffu, req));
+        int inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (j < T) off[j + 1] = carry + inc;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    for (int j = 0; j < T; ++j) {
-        const double w = Q.weight[j];
-        const bool required = w > magic;                // webui.py:161  (1000 itself is NOT required)
-        if (required) ++n_required;
-        if (!touched) continue;
-        const int t = Q.term[j];
-        const int64_t a = sl[(int64_t)j * (n_tiles + 1)], b = sl[(int64_t)j * (n_tiles + 1) + 1];
-        if (w < 0.0) {
-            // webui.py:154-160: docs CONTAINING the term -> -inf, nothing added
-            for (int64_t p = a + tid; p < b; p += BM25_THREADS) excl[post_doc[p] - lo] = 1;
+    if (lane == 0) off[0] = 0;
+    const int E = carry;
+    __syncwarp();
+
+    if (E > 0) {
+        for (int i = lane; i < BM25_SUB; i += 32) { acc[i] = 0.0; excl[i] = 0; reqc[i] = 0; }
+        __syncwarp();
+        if (E <= BM25_STAGE) {
+            // ---- stage every posting of the sub-tile with its contribution (all global loads independent) ----
+            for (int e = lane; e < E; e += 32) {
+                int j = 0;
+                while (e >= off[j + 1]) ++j;
+                const int64_t p = sl_a[j] + (e - off[j]);
+                const int d = A.post_doc[p];
+                const double w = Q.weight[j];
+                double c = 0.0;
+                if (!(w < 0.0)) {
+                    const int t = Q.term[j];
+                    const double mult = (w > A.magic) ? (w - A.magic) : w;
+                    const double idfv = (t >= 0 && t < A.n_vocab) ? A.idf[t] : 0.0;
+                    const double tf = A.post_tf ? (double)A.post_tf[p] : 1.0;
+                    const double denom = __dadd_rn(tf, A.kd[d]);                       // webui.py:145
+                    const double numer = __dmul_rn(tf, A.k1p1);                        // webui.py:146
+                    const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));     // webui.py:147
+                    c = __dmul_rn(mult, score);                                        // webui.py:167,170
+                }
+                st_doc[e] = (uint8_t)(d - lo);
+                st_val[e] = c;
+            }
+            __syncwarp();
+            // ---- ordered accumulation, shared memory only (doc ids are unique inside a term) ----
+            for (int j = 0; j < T; ++j) {
+                const double w = Q.weight[j];
+                const bool required = w > A.magic;
+                for (int e = off[j] + lane; e < off[j + 1]; e += 32) {
+                    const int l = st_doc[e];
+                    if (w < 0.0) excl[l] = 1;                                          // webui.py:154-160
+                    else {
+                        acc[l] = __dadd_rn(acc[l], st_val[e]);
+                        if (required) reqc[l] = (uint8_t)(reqc[l] + 1);
+                    }
+                }
+                __syncwarp();
+            }
         } else {
-            const double mult = required ? (w - magic) : w;
-            const double idfv = (t >= 0 && t < n_vocab) ? idf[t] : 0.0;
-            for (int64_t p = a + tid; p < b; p += BM25_THREADS) {
-                const int d = post_doc[p];
-                const double tf = post_tf ? (double)post_tf[p] : 1.0;
-                const double denom = __dadd_rn(tf, kd[d]);                       // webui.py:145
-                const double numer = __dmul_rn(tf, k1p1);                        // webui.py:146
-                const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));   // webui.py:147
-                const int l = (int)(d - lo);
-                acc[l] = __dadd_rn(acc[l], __dmul_rn(mult, score));              // webui.py:167,170
-                if (required) reqc[l] = (uint8_t)(reqc[l] + 1);
+            // ---- direct path for very dense sub-tiles ----
+            for (int j = 0; j < T; ++j) {
+                const double w = Q.weight[j];
+                const int t = Q.term[j];
+                const int64_t a = sl_a[j], b = a + (off[j + 1] - off[j]);
+                if (w < 0.0) {
+                    for (int64_t p = a + lane; p < b; p += 32) excl[A.post_doc[p] - lo] = 1;
+                } else {
+                    const bool required = w > A.magic;
+                    const double mult = required ? (w - A.magic) : w;
+                    const double idfv = (t >= 0 && t < A.n_vocab) ? A.idf[t] : 0.0;
+                    for (int64_t p = a + lane; p < b; p += 32) {
+                        const int d = A.post_doc[p];
+                        const double tf = A.post_tf ? (double)A.post_tf[p] : 1.0;
+                        const double denom = __dadd_rn(tf, A.kd[d]);
+                        const double numer = __dmul_rn(tf, A.k1p1);
+                        const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));
+                        const int l = (int)(d - lo);
+                        acc[l] = __dadd_rn(acc[l], __dmul_rn(mult, score));
+                        if (required) reqc[l] = (uint8_t)(reqc[l] + 1);
+                    }
+                }
+                __syncwarp();
             }
         }
-        __syncthreads();
     }
+    // a sub-tile no term touches: every doc scores +0.0, or -inf when the query has a required term
+    const double untouched = n_required > 0 ? -INFINITY : 0.0;
 
-    uint64_t best = dkey(-INFINITY);
-    if (touched) {
-        for (int64_t d = lo + tid; d < hi; d += BM25_THREADS) {
+    // webui.py:160,168: excluded hit, or a required term missing -> -inf (absorbing under +=)
+    if (PHASE == 0) {
+        if (E == 0 && !A.dense_out) {
+            // every doc of the sub-tile scores `untouched`; one relaxed check instead of 256 identical keys
+            const uint64_t k = dkey(untouched);
+            if (lane == 0 && k > *(volatile uint64_t*)&A.max_keys[qi])
+                atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)k);
+            return;
+        }
+        uint64_t best = dkey(-INFINITY);
+        for (int64_t d = lo + lane; d < hi; d += 32) {
             const int l = (int)(d - lo);
-            // webui.py:160,168: excluded hit, or a required term missing -> -inf (absorbing under +=)
-            const double v = (excl[l] || reqc[l] != n_required) ? -INFINITY : acc[l];
-            out[(int64_t)qi * ld + d] = v;
+            const double v = E > 0 ? ((excl[l] || reqc[l] != n_required) ? -INFINITY : acc[l]) : untouched;
+            if (A.dense_out) A.dense_out[(int64_t)qi * A.ld + d] = v;
             const uint64_t k = dkey(v);
             best = k > best ? k : best;
         }
-    } else {
-        // untouched tile: every doc scores +0.0, or -inf when the query has a required term (all of them lack it)
-        const double v = n_required > 0 ? -INFINITY : 0.0;
-        for (int64_t d = lo + tid; d < hi; d += BM25_THREADS) out[(int64_t)qi * ld + d] = v;
-        if (lo < hi) best = dkey(v);
+        best = warp_max_u64(best);
+        if (lane == 0 && best > *(volatile uint64_t*)&A.max_keys[qi])
+            atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)best);
+        return;
+    }
+
+    // ---- phase 1: bm25 / max (the docs that carry a contribution are compacted first so that the fp64 division
+    //      runs with full warps), then 0.5*bm25n + 0.5*simn ----
+    const double maxb = A.maxes[2 * qi];
+    const float maxs = (float)A.maxes[2 * qi + 1];
+    if (E > 0 && maxb > 0.0) {
+        int nn = 0;
+        for (int i = lane; i < BM25_SUB; i += 32) {
+            const bool nd = acc[i] != 0.0 && !excl[i] && reqc[i] == n_required;
+            const unsigned m = __ballot_sync(0xffffffffu, nd);
+            if (nd) need[nn + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
+            nn += __popc(m);
+        }
+        __syncwarp();
+        for (int i = lane; i < nn; i += 32) {
+            const int l = need[i];
+            acc[l] = __ddiv_rn(acc[l], maxb);                                     // webui.py:379-380
+        }
+        __syncwarp();
+    }
+    uint64_t best = KEY_EMPTY;
+    const float* simq = A.sim + (int64_t)qi * A.ld;
+    double* finq = A.fin + (int64_t)qi * A.ld;
+    if (E == 0) {
+        // untouched sub-tile: bm25n is the same for all its docs (0 / max = 0, -inf / max = -inf)
+        const double wbb = __dmul_rn(A.wb, untouched);
+        float sv[BM25_SUB / 32];
+#pragma unroll
+        for (int u = 0; u < BM25_SUB / 32; ++u) {
+            const int64_t d = lo + u * 32 + lane;
+            sv[u] = d < hi ? __ldcs(simq + d) : 0.0f;
+        }
+        double fbest = -INFINITY;
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < BM25_SUB / 32; ++u) {
+            const int64_t d = lo + u * 32 + lane;
+            if (d < hi) {
+                float sn = sv[u];
+                if (maxs > 0.0f) sn = __fdiv_rn(sn, maxs);
+                const double f = __dadd_rn(wbb, (double)__fmul_rn(A.wd, sn));
+                __stcs(finq + d, f);
+                fbest = any ? fmax(fbest, f) : f;          // no NaNs on this path unless the rows hold them
+                any = true;
+            }
+        }
+        best = any ? dkey(fbest) : KEY_EMPTY;
+        best = warp_max_u64(best);
+        if (lane == 0 && best != KEY_EMPTY)
+            atomicMax(reinterpret_cast<unsigned long long*>(&A.seg_max[(size_t)qi * 2048 + (int)(sub % A.seg_mod)]),
+                      (unsigned long long)best);
+        return;
+    }
+    for (int64_t d = lo + lane; d < hi; d += 32) {
+        const int l = (int)(d - lo);
+        const double b = (excl[l] || reqc[l] != n_required) ? -INFINITY : acc[l];
+        float s = __ldcs(simq + d);
+        if (maxs > 0.0f) s = __fdiv_rn(s, maxs);                                   // webui.py:377-378 (fp32 / fp32)
+        const double f = __dadd_rn(__dmul_rn(A.wb, b), (double)__fmul_rn(A.wd, s));   // webui.py:383
+        __stcs(finq + d, f);
+        const uint64_t k = dkey(f);
+        best = k > best ? k : best;
     }
     best = warp_max_u64(best);
-    if ((tid & 31) == 0) wmax[tid >> 5] = best;
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < BM25_THREADS / 32; ++w) best = wmax[w] > best ? wmax[w] : best;
-        atomicMax(reinterpret_cast<unsigned long long*>(&max_keys[qi]), (unsigned long long)best);
-    }
+    if (lane == 0 && best != KEY_EMPTY)
+        atomicMax(reinterpret_cast<unsigned long long*>(&A.seg_max[(size_t)qi * 2048 + (int)(sub % A.seg_mod)]),
+                  (unsigned long long)best);
 }
 
 }  // namespace ais

@@ -145,6 +145,7 @@ struct ais_engine {
     Buf out_ids, out_scores, out_count, out_amb;
     Buf fs_keys, fs_ids, fs_count;
     Buf bm25_slices;
+    int bm25_t_cap = 1;
     Buf seg_max, sel_thr, surv_count, surv_keys, surv_ids, gate, witness, last_keys, wit_table;
     uint64_t* h_last_keys = nullptr;
     int sel_k_cap = 0, out_topn_cap = 0;
@@ -217,7 +218,6 @@ int ensure_work(ais_engine* e) {
     const int64_t l = ld > e->ld ? ld : e->ld;
     TRY(dev_alloc(e, e->sim, (size_t)q * l * sizeof(float)));
     TRY(dev_alloc(e, e->rer, (size_t)q * l * sizeof(float)));
-    TRY(dev_alloc(e, e->bm25, (size_t)q * l * sizeof(double)));
     TRY(dev_alloc(e, e->fin, (size_t)q * l * sizeof(double)));
     TRY(dev_alloc(e, e->d_q, (size_t)q * DIM * sizeof(float)));
     TRY(dev_alloc(e, e->d_q2, (size_t)q * DIM * sizeof(float)));
@@ -375,7 +375,8 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<8>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
-    CK(cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
+    CK(cudaFuncSetAttribute(bm25_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
+    CK(cudaFuncSetAttribute(bm25_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
     return AIS_OK;
 }
@@ -404,21 +405,63 @@ int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bo
     return AIS_OK;
 }
 
-int launch_bm25(ais_engine* e, int nq) {
+Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
+    Bm25Args a;
+    memset(&a, 0, sizeof(a));
+    a.slices = e->bm25_slices.as<int64_t>();
+    a.t_cap = e->bm25_t_cap;
+    a.n_sub = n_sub;
+    a.post_doc = e->post_doc.as<int32_t>();
+    a.post_tf = e->has_tf ? e->post_tf.as<int32_t>() : nullptr;
+    a.idf = e->idf.as<double>();
+    a.kd = e->kd.as<double>();
+    a.n = e->n_bm25;
+    a.n_vocab = e->n_vocab;
+    a.queries = e->d_qt.as<QueryTerms>();
+    a.magic = e->p.require_magic;
+    a.k1p1 = e->p.k1 + 1.0;
+    a.ld = e->ld;
+    return a;
+}
+
+// phase 0 of the BM25 side: slice table + per-query maximum (dense scores only for the compute_bm25_scores seam)
+int launch_bm25_max(ais_engine* e, int nq, double* dense_out) {
     if (e->n_bm25 <= 0) return AIS_OK;
-    const int64_t n_tiles = (e->n_bm25 + BM25_TILE - 1) / BM25_TILE;
+    const int64_t n_sub = (e->n_bm25 + BM25_SUB - 1) / BM25_SUB;
     int t_cap = 1;
     for (int q = 0; q < nq; ++q) t_cap = e->h_qt[q].n_terms > t_cap ? e->h_qt[q].n_terms : t_cap;
-    TRY(dev_alloc(e, e->bm25_slices, (size_t)e->qt_cap * t_cap * (n_tiles + 1) * sizeof(int64_t)));
-    bm25_slices_kernel<<<dim3((unsigned)((n_tiles + 1 + 127) / 128), (unsigned)(nq * t_cap)), 128, 0, e->stream>>>(
-        e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->n_vocab, e->d_qt.as<QueryTerms>(), t_cap, n_tiles,
+    e->bm25_t_cap = t_cap;
+    TRY(dev_alloc(e, e->bm25_slices, (size_t)e->qt_cap * t_cap * (n_sub + 1) * sizeof(int64_t)));
+    bm25_slices_kernel<<<dim3((unsigned)((n_sub + 1 + 127) / 128), (unsigned)(nq * t_cap)), 128, 0, e->stream>>>(
+        e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->n_vocab, e->d_qt.as<QueryTerms>(), t_cap, n_sub,
         e->bm25_slices.as<int64_t>());
     LAUNCHED(e);
-    dim3 grid((unsigned)n_tiles, (unsigned)nq);
-    bm25_kernel<<<grid, BM25_THREADS, BM25_SMEM, e->stream>>>(
-        e->bm25_slices.as<int64_t>(), t_cap, n_tiles, e->post_doc.as<int32_t>(), e->has_tf ? e->post_tf.as<int32_t>() : nullptr,
-        e->idf.as<double>(), e->kd.as<double>(), e->n_bm25, e->n_vocab, e->d_qt.as<QueryTerms>(), e->p.require_magic,
-        e->p.k1 + 1.0, e->bm25.as<double>(), e->ld, e->maxb_key.as<uint64_t>());
+    Bm25Args a = bm25_args(e, n_sub);
+    a.max_keys = e->maxb_key.as<uint64_t>();
+    a.dense_out = dense_out;
+    bm25_warp_kernel<0><<<dim3((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq), BM25_THREADS, BM25_SMEM, e->stream>>>(a);
+    LAUNCHED(e);
+    return AIS_OK;
+}
+
+// phase 1: BM25 again (shared memory only), normalise, combine with the dot scores, store the combined scores and the
+// segment maxima the streaming select starts from.  Needs the slice table of launch_bm25_max for the same batch.
+int launch_bm25_combine(ais_engine* e, int nq, const double* d_maxes, int* n_seg_out) {
+    const int64_t n_sub = (e->n_bm25 + BM25_SUB - 1) / BM25_SUB;
+    int64_t segs = n_sub;
+    if (segs > SEG_MAX) segs = SEG_MAX;
+    *n_seg_out = (int)segs;
+    CK(cudaMemsetAsync(e->seg_max.p, 0, (size_t)nq * SEG_MAX * sizeof(uint64_t), e->stream));
+    if (e->n_bm25 <= 0) return AIS_OK;
+    Bm25Args a = bm25_args(e, n_sub);
+    a.sim = e->sim.as<float>();
+    a.fin = e->fin.as<double>();
+    a.maxes = d_maxes;
+    a.wb = e->p.bm25_weight;
+    a.wd = (float)e->p.doc2vec_weight;
+    a.seg_max = e->seg_max.as<uint64_t>();
+    a.seg_mod = (int)segs;
+    bm25_warp_kernel<1><<<dim3((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq), BM25_THREADS, BM25_SMEM, e->stream>>>(a);
     LAUNCHED(e);
     return AIS_OK;
 }
@@ -456,7 +499,7 @@ int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, 
     TRY(ensure_sel(e, k));
     const int64_t n = e->n();
     SelectArgs a;
-    a.sim = e->sim.as<float>(); a.bm25 = e->bm25.as<double>(); a.fin = e->fin.as<double>(); a.rer = e->rer.as<float>();
+    a.sim = e->sim.as<float>(); a.fin = e->fin.as<double>(); a.rer = e->rer.as<float>();
     a.n = n; a.ld = e->ld; a.id_base = e->first_doc;
     a.cp = combine_params(e);
     a.maxes = d_maxes;
@@ -474,10 +517,12 @@ int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, 
     a.surv_keys = e->surv_keys.as<uint64_t>();
     a.surv_ids = e->surv_ids.as<int64_t>();
     a.gate = e->gate.as<int>();
-    if (n > 0) {
+    if (mode == 0) {
+        // pass 1: the BM25 tile kernel's second phase forms the combined scores and the segment maxima in one go
+        TRY(launch_bm25_combine(e, nq, d_maxes, &a.n_seg));
+    } else if (n > 0) {
         const dim3 g1((unsigned)((S + SEG_WARPS - 1) / SEG_WARPS), (unsigned)nq);
-        if (mode == 0) segmax_kernel<0><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
-        else if (mode == 1) segmax_kernel<1><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
+        if (mode == 1) segmax_kernel<1><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
         else segmax_kernel<2><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
         LAUNCHED(e);
     }
@@ -496,11 +541,7 @@ int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, 
     // gated fallback (runs only for queries whose survivors overflowed)
     const int G = sel_blocks(e);
     const int* gate = e->gate.as<int>();
-    if (mode == 0)
-        combine_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
-            e->sim.as<float>(), e->bm25.as<double>(), e->fin.as<double>(), n, e->ld, d_maxes, a.cp, e->first_doc, k,
-            e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
-    else if (mode == 1)
+    if (mode == 0 || mode == 1)       // pass 1 has stored its combined scores by now
         final_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(e->fin.as<double>(), n, e->ld, e->first_doc, k,
                                                                        e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
     else
@@ -521,7 +562,7 @@ int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
     init_keys_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
                                              e->maxr_key.as<uint64_t>(), e->status.as<int32_t>(), nq, 1);
     LAUNCHED(e);
-    TRY(launch_bm25(e, nq));
+    TRY(launch_bm25_max(e, nq, nullptr));
     TRY(launch_scan(e, e->d_q.as<float>(), nq, e->sim.as<float>(), e->maxs_key.as<uint32_t>()));
     maxes_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxb_key.as<uint64_t>(), e->maxs_key.as<uint32_t>(), nq, d_maxes);
     LAUNCHED(e);
@@ -1094,7 +1135,8 @@ int ais_bm25_scores(ais_engine* e, const int32_t* term_ids, const double* weight
     init_keys_kernel<<<1, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(), e->maxr_key.as<uint64_t>(),
                                              e->status.as<int32_t>(), 1, 1);
     LAUNCHED(e);
-    TRY(launch_bm25(e, 1));
+    TRY(dev_alloc(e, e->bm25, (size_t)e->ld * sizeof(double)));
+    TRY(launch_bm25_max(e, 1, e->bm25.as<double>()));
     CK(cudaMemcpyAsync(out, e->bm25.p, (size_t)e->n_bm25 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return AIS_OK;
@@ -1271,7 +1313,7 @@ int ais_debug_read(ais_engine* e, int32_t which, int32_t query, void* out) {
     DeviceGuard g(e->device);
     const size_t n = (size_t)e->n();
     const void* src = which == 0 ? (const void*)(e->sim.as<float>() + (size_t)query * e->ld)
-                    : which == 1 ? (const void*)(e->bm25.as<double>() + (size_t)query * e->ld)
+                    : which == 1 ? (const void*)(e->bm25.as<double>())
                     : which == 2 ? (const void*)(e->fin.as<double>() + (size_t)query * e->ld)
                                  : (const void*)(e->rer.as<float>() + (size_t)query * e->ld);
     CK(cudaMemcpyAsync(out, src, n * ((which == 0 || which == 3) ? 4 : 8), cudaMemcpyDeviceToHost, e->stream));

@@ -1,8 +1,8 @@
 // Streaming threshold select (the fast path of the top-k stages) and the near-tie witness pass.
 //
 // Exact top-k of N keys in three light passes, none of which synchronises inside its loop:
-//   1. segmax:    the docs are cut into S <= 2048 contiguous segments; one warp per segment streams its
-//                 docs (computing the combined score on the fly) and records the segment's best key.
+//   1. segmax:    the docs are cut into S <= 2048 segments; one warp per segment streams its docs and records
+//                 the segment's best key (pass 1: done by the BM25 tile kernel's combine phase, bm25.cuh).
 //   2. threshold: T = k-th largest segment maximum.  At least k docs (one per such segment) have
 //                 key >= T, so the global top-k is contained in {key >= T}; with docs spread over the
 //                 segments |{key >= T}| ~ -S ln(1 - k/S), i.e. barely more than k.
@@ -27,21 +27,6 @@ constexpr int SURV_CAP = 4096;
 constexpr int COLLECT_THREADS = 256;
 
 // ---- score functors: key of doc i, false if the doc is not a candidate ---------------------------
-struct ScoreCombine {      // pass 1: webui.py:376-383, also stores the combined score
-    const float* sim; const double* bm25; double* fin; float maxs; double maxb; CombineParams cp;
-    __device__ __forceinline__ bool operator()(int64_t i, int64_t, uint64_t& key) const {
-        float s = __ldcs(sim + i);          // read once: streaming loads / stores keep L2 for the posting lists
-        double b = __ldcs(bm25 + i);
-        if (maxs > 0.0f) s = __fdiv_rn(s, maxs);
-        // 0 / max = 0 and -inf / max = -inf exactly: only docs with a BM25 contribution pay for the fp64 division
-        if (maxb > 0.0 && b != 0.0 && b != -INFINITY) b = __ddiv_rn(b, maxb);
-        const double f = __dadd_rn(__dmul_rn(cp.wb, b), (double)__fmul_rn(cp.wd, s));
-        __stcs(fin + i, f);
-        key = dkey(f);
-        return true;
-    }
-    __device__ __forceinline__ bool is_seed(int64_t) const { return false; }
-};
 struct ScoreFinal {        // stored combined scores
     const double* fin;
     __device__ __forceinline__ bool operator()(int64_t i, int64_t, uint64_t& key) const {
@@ -65,7 +50,7 @@ struct ScoreRerank {       // pass 2: webui.py:208 blend; the PRF seeds are not 
 };
 
 struct SelectArgs {        // everything the three kernels share
-    const float* sim; const double* bm25; double* fin; const float* rer;
+    const float* sim; double* fin; const float* rer;
     int64_t n, ld, id_base;
     CombineParams cp;
     const double* maxes;        // [nq][2] (mode 0)
@@ -84,11 +69,7 @@ struct SelectArgs {        // everything the three kernels share
 
 template <int MODE, typename Body>
 __device__ __forceinline__ void with_functor(const SelectArgs& a, int qi, const int64_t* seeds_smem, Body&& body) {
-    if (MODE == 0) {
-        ScoreCombine f{a.sim + (size_t)qi * a.ld, a.bm25 + (size_t)qi * a.ld, a.fin + (size_t)qi * a.ld,
-                       (float)a.maxes[2 * qi + 1], a.maxes[2 * qi], a.cp};
-        body(f);
-    } else if (MODE == 1) {
+    if (MODE == 1) {
         ScoreFinal f{a.fin + (size_t)qi * a.ld};
         body(f);
     } else {
@@ -200,7 +181,7 @@ collect_kernel(SelectArgs a) {
     int64_t* si = a.surv_ids + (size_t)qi * SURV_CAP;
     const int64_t stride = (int64_t)gridDim.x * COLLECT_THREADS;
     const int64_t n_round = ((a.n + 31) / 32) * 32;          // whole warps stay together for the ballots
-    with_functor<(MODE == 0 ? 1 : MODE)>(a, qi, seeds, [&](auto& f) {   // pass 1 re-reads the stored finals
+    with_functor<MODE>(a, qi, seeds, [&](auto& f) {
         for (int64_t i0 = (int64_t)blockIdx.x * COLLECT_THREADS + threadIdx.x; i0 < n_round; i0 += 4 * stride) {
             uint64_t key[4];
             bool pass[4];

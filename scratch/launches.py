@@ -4,7 +4,7 @@ for f in sys.argv[1:]:
     hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value")
     seq=[(r[ki].split("(")[0].replace("ais::","").replace("<unnamed>::","").replace("void ",""), float(r[vi].replace(",",""))) for r in rows[1:]]
     # split into steps at init_keys preceded by non-init... find indices of 'bm25_kernel'
-    starts=[i-1 for i,(n,_) in enumerate(seq) if n.startswith("bm25_kernel")]
+    starts=[max(i-1,0) for i,(n,_) in enumerate(seq) if n.startswith("bm25_slices")]
     last=seq[starts[-1]:]
     tot=sum(v for _,v in last)
     print(f, "launches in last step", len(last), "sum us %.1f"%(tot/1e3))
