@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--cpu-sample-docs", type=int, default=100_000)
     ap.add_argument("--cpu-queries", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the extra batch-1 / batch-4 operating points")
     ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1,2,4,8,16 (extra key batch_sweep)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -281,9 +282,13 @@ def main():
     step_gbs = step_bytes / (dev_ms / args.steps * 1e-3) / 1e9
 
     sweep = None
-    if args.sweep:
+    if args.sweep or not args.no_modes:
+        # other operating points of the same engine: batch 1 = single-query latency mode (both scans at the HBM
+        # roofline), batch 4 = largest batch of the fp32 SIMT scan; --sweep adds the rest
         sweep = {}
-        for bb in (1, 2, 4, 8, 16, 32, 64):
+        for bb in ((1, 2, 4, 8, 16, 32, 64) if args.sweep else (1, 4)):
+            if bb > eng.params.max_batch:
+                break
             run_steps(2, bb, 0)
             eng.set_profiling(True); eng.reset_stats()
             ms, wms, _, _, _, _ = run_steps(max(4, args.steps // 2), bb, 2)
@@ -291,7 +296,9 @@ def main():
             k = max(4, args.steps // 2)
             sm = s2["scan_ms_total"] / max(1, s2["scan_launches"])
             sweep[str(bb)] = {"qps": k * bb / (ms * 1e-3), "e2e_qps": k * bb / (wms * 1e-3), "scan_ms": sm,
-                              "scan_gbs": scan_bytes / (sm * 1e-3) / 1e9, "scan_share": s2["scan_ms_total"] / ms}
+                              "scan_gbs": scan_bytes / (sm * 1e-3) / 1e9, "scan_frac_of_peak": scan_bytes / (sm * 1e-3) / 1e9 / peak,
+                              "scan_share": s2["scan_ms_total"] / ms,
+                              "whole_step_frac_of_peak": (2 * scan_bytes * bb) / (ms / k * 1e-3) / 1e9 / peak / bb}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -327,7 +334,7 @@ def main():
             "index_build_s": t_build,
         }
         if sweep:
-            line["batch_sweep"] = sweep
+            line["batch_sweep" if args.sweep else "other_batch_sizes"] = sweep
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
