@@ -62,6 +62,9 @@ SIGNATURES = {
     "ais_reserve_docs": (C.c_int, [_vp, _i64]),
     "ais_vectors_device_ptr": (C.c_int, [_vp, _i64, C.POINTER(_vp)]),
     "ais_load_bm25": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _dbl]),
+    "ais_build_bm25": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "ais_finish_bm25": (C.c_int, [_vp, _vp, _dbl]),
+    "ais_export_postings": (C.c_int, [_vp, _vp, _vp, _vp]),
     "ais_dot_scores": (C.c_int, [_vp, _vp, _vp]),
     "ais_bm25_scores": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "ais_final_scores": (C.c_int, [_vp, C.POINTER(AisQuery), _vp]),

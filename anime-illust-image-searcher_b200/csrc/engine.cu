@@ -21,6 +21,7 @@
 
 #include "../../include/ais_b200.h"
 #include "bm25.cuh"
+#include "build.cuh"
 #include "common.cuh"
 #include "scan.cuh"
 #include "select.cuh"
@@ -134,7 +135,7 @@ struct ais_engine {
     double avgdl = 0.0;
     bool has_tf = false;
     int32_t n_vocab = 0;
-    int64_t n_bm25 = -1, n_post = 0;
+    int64_t n_bm25 = -1, n_post = 0, n_built = -1;
 
     // per-batch work
     int qt_cap = 0;
@@ -1105,6 +1106,107 @@ int ais_load_bm25(ais_engine* e, const int64_t* post_ptr, const int32_t* post_do
     e->n_vocab = n_terms;
     e->n_bm25 = n_docs;
     e->n_post = n_post;
+    return AIS_OK;
+}
+
+// ---- BM25 index build (genmodel.py:51-99) -------------------------------------------------------------------
+int ais_build_bm25(ais_engine* e, const int64_t* seq_ptr, const int32_t* seq_ids, int64_t n_docs, int32_t n_terms,
+                   int64_t* out_df, int64_t* out_doc_len) {
+    if (!e || !seq_ptr || n_docs < 0 || n_terms < 1) return fail(AIS_ERR_INVALID, "bad argument");
+    if (n_docs >= (1LL << 31)) return fail(AIS_ERR_UNSUPPORTED, "a shard holds at most 2^31-1 docs (int32 local doc ids)");
+    DeviceGuard g(e->device);
+    Buf d_ptr, d_ids, d_cnt, d_df, d_err;
+    int st = AIS_OK;
+    auto body = [&]() -> int {
+        TRY(dev_alloc(e, d_ptr, (size_t)(n_docs + 1) * sizeof(int64_t)));
+        CK(cudaMemcpyAsync(d_ptr.p, seq_ptr, (size_t)(n_docs + 1) * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+        int64_t n_tok = 0;
+        CK(cudaMemcpyAsync(&n_tok, (const char*)d_ptr.p + (size_t)n_docs * sizeof(int64_t), sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (n_tok < 0 || (n_tok > 0 && !seq_ids)) return fail(AIS_ERR_INVALID, "bad token sequence");
+        TRY(dev_alloc(e, d_ids, (size_t)n_tok * sizeof(int32_t)));
+        if (n_tok > 0) CK(cudaMemcpyAsync(d_ids.p, seq_ids, (size_t)n_tok * sizeof(int32_t), cudaMemcpyDefault, e->stream));
+        int64_t docs_per_cta = 1024;
+        const int64_t max_ctas = 4LL * e->sm_count;
+        if ((n_docs + docs_per_cta - 1) / docs_per_cta > max_ctas) docs_per_cta = (n_docs + max_ctas - 1) / max_ctas;
+        const int n_ctas = (int)((n_docs + docs_per_cta - 1) / docs_per_cta);
+        TRY(dev_alloc(e, d_cnt, (size_t)(n_ctas > 0 ? n_ctas : 1) * n_terms * sizeof(int32_t)));
+        TRY(dev_alloc(e, d_df, (size_t)n_terms * sizeof(int64_t)));
+        TRY(dev_alloc(e, d_err, sizeof(int)));
+        TRY(dev_alloc(e, e->doc_len, (size_t)n_docs * sizeof(int64_t)));
+        TRY(dev_alloc(e, e->post_ptr, (size_t)(n_terms + 1) * sizeof(int64_t)));
+        CK(cudaMemsetAsync(d_cnt.p, 0, (size_t)(n_ctas > 0 ? n_ctas : 1) * n_terms * sizeof(int32_t), e->stream));
+        CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), e->stream));
+        if (n_ctas > 0) {
+            build_count_kernel<<<n_ctas, BUILD_THREADS, 0, e->stream>>>(d_ptr.as<int64_t>(), d_ids.as<int32_t>(), n_docs, docs_per_cta,
+                                                                       n_terms, d_cnt.as<int32_t>(), e->doc_len.as<int64_t>(), d_err.as<int>());
+            LAUNCHED(e);
+        }
+        build_scan_kernel<<<(n_terms + 127) / 128, 128, 0, e->stream>>>(d_cnt.as<int32_t>(), n_ctas, n_terms, d_df.as<int64_t>());
+        LAUNCHED(e);
+        build_ptr_kernel<<<1, 32, 0, e->stream>>>(d_df.as<int64_t>(), n_terms, e->post_ptr.as<int64_t>());
+        LAUNCHED(e);
+        int err = 0;
+        int64_t n_post = 0;
+        CK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(&n_post, (const char*)e->post_ptr.p + (size_t)n_terms * sizeof(int64_t), sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (err == 1) return fail(AIS_ERR_UNSUPPORTED, "a doc has more than %d tags", BUILD_MAX_DOC_TAGS);
+        if (err == 2) return fail(AIS_ERR_INVALID, "term id outside [0, %d)", n_terms);
+        TRY(dev_alloc(e, e->post_doc, (size_t)n_post * sizeof(int32_t)));
+        TRY(dev_alloc(e, e->post_tf, (size_t)n_post * sizeof(int32_t)));
+        if (n_ctas > 0) {
+            build_fill_kernel<<<n_ctas, BUILD_THREADS, 0, e->stream>>>(d_ptr.as<int64_t>(), d_ids.as<int32_t>(), n_docs, docs_per_cta, n_terms,
+                                                                      d_cnt.as<int32_t>(), e->post_ptr.as<int64_t>(),
+                                                                      e->post_doc.as<int32_t>(), e->post_tf.as<int32_t>());
+            LAUNCHED(e);
+        }
+        if (out_df) CK(cudaMemcpyAsync(out_df, d_df.p, (size_t)n_terms * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+        if (out_doc_len && n_docs > 0)
+            CK(cudaMemcpyAsync(out_doc_len, e->doc_len.p, (size_t)n_docs * sizeof(int64_t), cudaMemcpyDefault, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->has_tf = true;
+        e->n_vocab = n_terms;
+        e->n_post = n_post;
+        e->n_bm25 = -1;                 // scoring needs ais_finish_bm25 (IDF table, avgdl) first
+        e->n_built = n_docs;
+        return AIS_OK;
+    };
+    st = body();
+    for (Buf* b : {&d_ptr, &d_ids, &d_cnt, &d_df, &d_err}) dev_free(e, *b);
+    return st;
+}
+
+int ais_finish_bm25(ais_engine* e, const double* idf, double avgdl) {
+    if (!e || !idf) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (e->n_built < 0) return fail(AIS_ERR_NOT_LOADED, "ais_build_bm25 has not run");
+    DeviceGuard g(e->device);
+    const int64_t n_docs = e->n_built;
+    TRY(dev_alloc(e, e->idf, (size_t)e->n_vocab * sizeof(double)));
+    CK(cudaMemcpyAsync(e->idf.p, idf, (size_t)e->n_vocab * sizeof(double), cudaMemcpyDefault, e->stream));
+    TRY(dev_alloc(e, e->kd, (size_t)n_docs * sizeof(double)));
+    if (n_docs > 0) {
+        kd_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, e->stream>>>(e->doc_len.as<int64_t>(), n_docs, avgdl, e->p.k1, e->p.b,
+                                                                          1.0 - e->p.b, e->kd.as<double>());
+        LAUNCHED(e);
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    e->avgdl = avgdl;
+    e->n_bm25 = n_docs;
+    return AIS_OK;
+}
+
+int ais_export_postings(ais_engine* e, int64_t* post_ptr, int32_t* post_doc, int32_t* post_tf) {
+    if (!e || !post_ptr) return fail(AIS_ERR_INVALID, "NULL argument");
+    if (!e->post_ptr.p) return fail(AIS_ERR_NOT_LOADED, "no posting lists");
+    DeviceGuard g(e->device);
+    CK(cudaMemcpyAsync(post_ptr, e->post_ptr.p, (size_t)(e->n_vocab + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    if (post_doc && e->n_post > 0) CK(cudaMemcpyAsync(post_doc, e->post_doc.p, (size_t)e->n_post * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (post_tf && e->n_post > 0) {
+        if (!e->has_tf) return fail(AIS_ERR_INVALID, "the index was loaded without tf (every tf is 1)");
+        CK(cudaMemcpyAsync(post_tf, e->post_tf.p, (size_t)e->n_post * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
     return AIS_OK;
 }
 

@@ -176,6 +176,34 @@ class SearchEngine:
                                 _ptr(doc_len), float(avgdl)))
         self.n_bm25 = n_docs
 
+    def build_bm25(self, seq_ptr, seq_ids, n_terms: int):
+        """gen_and_save_bm25_index (genmodel.py:51-99) on the GPU from the docs' term-id sequences (CSR).
+        -> (df int64[n_terms], doc_len int64[n_docs]); call finish_bm25(idf, avgdl) afterwards."""
+        seq_ptr = np.ascontiguousarray(seq_ptr, dtype=np.int64) if isinstance(seq_ptr, np.ndarray) else seq_ptr.contiguous()
+        seq_ids = np.ascontiguousarray(seq_ids, dtype=np.int32) if isinstance(seq_ids, np.ndarray) else seq_ids.contiguous()
+        n_docs = len(seq_ptr) - 1
+        df = np.zeros(n_terms, dtype=np.int64)
+        doc_len = np.zeros(n_docs, dtype=np.int64)
+        with self._lock:
+            check(lib.ais_build_bm25(self._h, _ptr(seq_ptr), _ptr(seq_ids), n_docs, n_terms, _ptr(df), _ptr(doc_len)))
+        self._n_built, self._v_built = n_docs, n_terms
+        return df, doc_len
+
+    def finish_bm25(self, idf: np.ndarray, avgdl: float) -> None:
+        idf = np.ascontiguousarray(idf, dtype=np.float64)
+        with self._lock:
+            check(lib.ais_finish_bm25(self._h, _ptr(idf), float(avgdl)))
+        self.n_bm25 = self._n_built
+
+    def export_postings(self, with_tf: bool = True):
+        ptr = np.zeros(self._v_built + 1, dtype=np.int64)
+        check(lib.ais_export_postings(self._h, _ptr(ptr), None, None))
+        n = int(ptr[-1])
+        doc = np.zeros(n, dtype=np.int32)
+        tf = np.zeros(n, dtype=np.int32) if with_tf else None
+        check(lib.ais_export_postings(self._h, _ptr(ptr), _ptr(doc), _ptr(tf)))
+        return ptr, doc, tf
+
     def set_shard(self, first_doc: int, n_total: int) -> None:
         check(lib.ais_set_shard(self._h, first_doc, n_total))
         self.first_doc, self.n_total = first_doc, n_total

@@ -89,15 +89,20 @@ class ShardedSearch:
         return getattr(eng, "torch_device", torch.device("cpu"))
 
     def _gather_lists(self, keys: List[torch.Tensor], ids: List[torch.Tensor]):
-        """per-engine [nq, k] -> [L, nq, k] with L = world * engines-per-process (on engine 0's device)."""
+        """per-engine [nq, k] -> [L, nq, k] with L = world * engines-per-process (on engine 0's device).
+        keys[j] / ids[j] are the two halves of ONE buffer (see _cand_buffers): a single all-gather moves both."""
         dev = self._dev(self.engines[0])
-        lk = torch.stack([k.to(dev) for k in keys])
-        li = torch.stack([i.to(dev) for i in ids])
-        gk = self.comm.all_gather(lk)
-        gi = self.comm.all_gather(li)
-        return gk.reshape((-1,) + tuple(lk.shape[1:])).contiguous(), gi.reshape((-1,) + tuple(li.shape[1:])).contiguous()
+        packs = [k._base if k._base is not None else torch.stack([k, i]) for k, i in zip(keys, ids)]   # [2, nq, k] each
+        local = packs[0].unsqueeze(0) if len(packs) == 1 else torch.stack([p.to(dev) for p in packs])   # [E, 2, nq, k]
+        g = self.comm.all_gather(local)                                                                  # [W, E, 2, nq, k]
+        g = g.reshape((-1,) + tuple(local.shape[1:]))                                                    # [L, 2, nq, k]
+        if g.shape[0] == 1:
+            return g[0, 0].unsqueeze(0), g[0, 1].unsqueeze(0)
+        return g[:, 0].contiguous(), g[:, 1].contiguous()
 
     def _reduce_local(self, tensors: List[torch.Tensor], op) -> torch.Tensor:
+        if len(tensors) == 1:
+            return tensors[0]
         dev = self._dev(self.engines[0])
         acc = tensors[0].to(dev).clone()
         for t in tensors[1:]:
@@ -105,9 +110,8 @@ class ShardedSearch:
         return acc
 
     def _cand_buffers(self, nq: int, k: int):
-        keys = [torch.empty((nq, k), dtype=torch.int64, device=self._dev(e)) for e in self.engines]
-        ids = [torch.empty((nq, k), dtype=torch.int64, device=self._dev(e)) for e in self.engines]
-        return keys, ids
+        packs = [torch.empty((2, nq, k), dtype=torch.int64, device=self._dev(e)) for e in self.engines]
+        return [p[0] for p in packs], [p[1] for p in packs]
 
     # ---- one batch ---------------------------------------------------------------------------------
     def search_raw(self, queries: Sequence[Query], topn: int, prf_mode: int, infer_cb: Optional[Callable] = None):

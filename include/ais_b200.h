@@ -135,6 +135,19 @@ int ais_load_bm25(ais_engine* e, const int64_t* post_ptr /*[n_terms+1]*/, const 
                   const int32_t* post_tf, int32_t n_terms, int64_t n_docs, const double* idf /*[n_terms]*/,
                   const int64_t* doc_len /*[n_docs]*/, double avgdl);
 
+/* --- index build: gen_and_save_bm25_index genmodel.py:51-99 on the GPU ------------------------ */
+/* From the docs' term-id sequences (doc-major CSR, csv tag order, repeats allowed; the host has already
+ * mapped tags through dictionary.token2id and dropped unknown ones, genmodel.py:59-61) build, on the device:
+ * doc lengths (genmodel.py:69), document frequencies (genmodel.py:72-73) and the tag-major posting lists with
+ * tf (the bm25_corpus dicts of genmodel.py:64-68, transposed).  out_df [n_terms] / out_doc_len [n_docs] are
+ * optional host-or-device outputs.  IDF (genmodel.py:79-82 uses numpy.log) and avgdl (numpy.mean) stay on the
+ * host for bit-exact parity: pass them to ais_finish_bm25, which makes the index searchable. */
+int ais_build_bm25(ais_engine* e, const int64_t* seq_ptr /*[n_docs+1]*/, const int32_t* seq_ids, int64_t n_docs,
+                   int32_t n_terms, int64_t* out_df, int64_t* out_doc_len);
+int ais_finish_bm25(ais_engine* e, const double* idf /*[n_terms], 0 where df == 0*/, double avgdl);
+/* posting lists as staged / built (host arrays; post_ptr [n_terms+1], post_doc / post_tf [post_ptr[n_terms]]) */
+int ais_export_postings(ais_engine* e, int64_t* post_ptr, int32_t* post_doc, int32_t* post_tf);
+
 /* --- test seams (full score vectors; they defeat fusion and are not the fast path) ---- */
 /* index[vec]  (webui.py:352, :205): out[N] fp32 = rows . q ; q is the dense unit query. */
 int ais_dot_scores(ais_engine* e, const float* q /*[dim] host*/, float* out /*[N] host*/);

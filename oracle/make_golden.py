@@ -106,6 +106,18 @@ def fixture_main():
     seam["terms_form_bm25"] = world.compute_bm25_scores(query_terms=[pop[0], pop[2], "no_such_tag"])
     seam["terms_form_tags"] = np.array([pop[0], pop[2], "no_such_tag"])
 
+    # what the reference's own gen_and_save_bm25_index (genmodel.py:51-99) produced for this corpus
+    ns = world.ns
+    corpus = ns["bm25_corpus"]
+    cptr = np.cumsum([0] + [len(d) for d in corpus]).astype(np.int64)
+    idf_dense = np.zeros(ix.vocab_size)
+    for t, v in ns["bm25_idf"].items():
+        idf_dense[t] = v
+    np.savez_compressed(os.path.join(OUT, "bm25_build_main.npz"),
+                        doc_lengths=np.asarray(ns["bm25_doc_lengths"]), avgdl=np.float64(ns["bm25_avgdl"]), D=np.int64(ns["bm25_D"]),
+                        idf=idf_dense, idf_terms=np.array(sorted(ns["bm25_idf"].keys()), dtype=np.int64),
+                        corpus_ptr=cptr, corpus_terms=np.array([t for d in corpus for t in d.keys()], dtype=np.int64),
+                        corpus_tfs=np.array([f for d in corpus for f in d.values()], dtype=np.int64))
     np.savez_compressed(os.path.join(OUT, "index_main.npz"), **index_arrays(ix))
     np.savez_compressed(os.path.join(OUT, "seams_main.npz"), **seam)
     with open(os.path.join(OUT, "results_main.json"), "w") as f:

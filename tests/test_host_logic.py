@@ -71,3 +71,18 @@ def test_shard_bounds_cover_everything():
             spans = [shard.shard_bounds(n, w, r) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_builder_host_side_matches_reference_outputs(main_index):
+    """tokens_to_csr / idf_table (the host half of the GPU BM25 builder) against the reference builder's outputs."""
+    import os
+    from golden_util import GOLDEN
+    from ais_b200 import genmodel_api as G
+    z = np.load(os.path.join(GOLDEN, "bm25_build_main.npz"))
+    ix = main_index
+    corpus = [[ix.tag_names[t] for t in seq] + ["unknown_tag"] for seq in ix.doc_tag_seq]
+    ptr, ids = G.tokens_to_csr(corpus, ix.token2id)
+    assert np.array_equal(np.diff(ptr), z["doc_lengths"])
+    assert np.array_equal(ids, np.concatenate(ix.doc_tag_seq))
+    idf = G.idf_table(ix.df, ix.n_docs)
+    assert sorted(idf) == z["idf_terms"].tolist() and all(idf[t] == z["idf"][t] for t in idf)
