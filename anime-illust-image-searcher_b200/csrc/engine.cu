@@ -24,6 +24,7 @@
 #include "build.cuh"
 #include "common.cuh"
 #include "scan.cuh"
+#include "scan_tc.cuh"
 #include "select.cuh"
 #include "select2.cuh"
 
@@ -162,6 +163,10 @@ struct ais_engine {
     int64_t scan_launches = 0, kernel_launches = 0, fullsort_fallbacks = 0, bytes_device = 0;
     bool profiling = false;
     bool use_mma = true;       // >= 5 queries per pass: tensor-core scan (3xTF32); AIS_SCAN_SIMT=1 keeps the fp32 SIMT kernel
+    int tc_min = 17;           // >= tc_min queries left in a batch: tcgen05 scan, 32 queries per pass (AIS_SCAN_TC_MIN; 0 = off)
+    Buf qsplit;                // [64][300] hi | lo images of the queries of one tcgen05 pass
+    CUtensorMap tm_rows, tm_q;
+    const void* tm_rows_ptr = nullptr;  int64_t tm_rows_n = -1;  const void* tm_q_ptr = nullptr;
     double scan_ms_total = 0.0;
     std::vector<cudaEvent_t> ev_pending, ev_free;
 
@@ -349,6 +354,71 @@ int launch_scan_mma_t(ais_engine* e, const float* d_q, int nq, float* out, uint3
     return AIS_OK;
 }
 
+// ---- tcgen05 scan: tensor maps (driver entry point fetched through the runtime, no libcuda link) --------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// [n_rows][300] fp32 row-major -> boxes of [box_rows][32 columns] landing in the K-major SWIZZLE_128B layout
+int make_row_tmap(CUtensorMap* tm, const void* ptr, int64_t n_rows, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(AIS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)DIM, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ROW_BYTES};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, elem,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AIS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return AIS_OK;
+}
+
+int launch_scan_tc(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
+    if (e->n_vec >= (1LL << 31)) return fail(AIS_ERR_INVALID, "tcgen05 scan: shard larger than 2^31 docs");
+    TRY(dev_alloc(e, e->qsplit, (size_t)2 * TC_N * DIM * sizeof(float)));
+    if (e->tm_q_ptr != e->qsplit.p) {
+        TRY(make_row_tmap(&e->tm_q, e->qsplit.p, 2 * TC_N, TC_N));
+        e->tm_q_ptr = e->qsplit.p;
+    }
+    if (e->tm_rows_ptr != e->rows.p || e->tm_rows_n != e->n_vec) {
+        TRY(make_row_tmap(&e->tm_rows, e->rows.p, e->n_vec, TC_M));
+        e->tm_rows_ptr = e->rows.p;
+        e->tm_rows_n = e->n_vec;
+    }
+    split_queries_kernel<<<(TC_N * DIM + 255) / 256, 256, 0, e->stream>>>(d_q, nq, e->qsplit.as<float>());
+    LAUNCHED(e);
+    const int64_t n_tiles = (e->n_vec + TC_M - 1) / TC_M;
+    const int grid = (int)(n_tiles < e->sm_count ? n_tiles : e->sm_count);
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (e->profiling) {
+        for (cudaEvent_t* ev : {&a, &b}) {
+            if (!e->ev_free.empty()) { *ev = e->ev_free.back(); e->ev_free.pop_back(); }
+            else CK(cudaEventCreate(ev));
+        }
+        CK(cudaEventRecord(a, e->stream));
+    }
+    scan_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, e->stream>>>(e->tm_rows, e->tm_q, e->n_vec, out, e->ld, max_keys, nq);
+    LAUNCHED(e);
+    e->scan_launches++;
+    if (e->profiling) {
+        CK(cudaEventRecord(b, e->stream));
+        e->ev_pending.push_back(a);
+        e->ev_pending.push_back(b);
+    }
+    return AIS_OK;
+}
+
 int launch_scan_one(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
     if (nq <= 1) return launch_scan_t<1>(e, d_q, nq, out, max_keys);
     if (nq <= 2) return launch_scan_t<2>(e, d_q, nq, out, max_keys);
@@ -361,9 +431,14 @@ int launch_scan_one(ais_engine* e, const float* d_q, int nq, float* out, uint32_
 // one pass over the rows per MAX_QT queries (the query buffer is zero-padded to a power of two >= nq)
 int launch_scan(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
     if (e->n_vec == 0) return AIS_OK;
-    for (int q0 = 0; q0 < nq; q0 += MAX_QT) {
-        const int m = nq - q0 < MAX_QT ? nq - q0 : MAX_QT;
-        TRY(launch_scan_one(e, d_q + (size_t)q0 * DIM, m, out + (size_t)q0 * e->ld, max_keys + q0));
+    for (int q0 = 0; q0 < nq;) {
+        const int left = nq - q0;
+        const bool tc = e->tc_min > 0 && left >= e->tc_min;
+        const int cap = tc ? TC_N : MAX_QT;
+        const int m = left < cap ? left : cap;
+        if (tc) TRY(launch_scan_tc(e, d_q + (size_t)q0 * DIM, m, out + (size_t)q0 * e->ld, max_keys + q0));
+        else TRY(launch_scan_one(e, d_q + (size_t)q0 * DIM, m, out + (size_t)q0 * e->ld, max_keys + q0));
+        q0 += m;
     }
     return AIS_OK;
 }
@@ -376,6 +451,7 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<8>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
+    CK(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CK(cudaFuncSetAttribute(bm25_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(bm25_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
@@ -975,6 +1051,7 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
     e->stream = e->own_stream;
     const char* simt = getenv("AIS_SCAN_SIMT");
     e->use_mma = !(simt && simt[0] == '1');
+    if (const char* tcm = getenv("AIS_SCAN_TC_MIN")) e->tc_min = atoi(tcm);
     int s = set_scan_attrs();
     if (s != AIS_OK) { cudaStreamDestroy(e->own_stream); delete e; return s; }
     *out = e;
@@ -990,7 +1067,7 @@ int ais_destroy(ais_engine* e) {
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
                    &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->sel_thr, &e->surv_count,
-                   &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices})
+                   &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices, &e->qsplit})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,
                     (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small, (void*)e->h_last_keys})

@@ -1,0 +1,348 @@
+// scan_tc_kernel: the doc-vector scan for 17..32 queries per pass on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, A operand and accumulators in TMEM, rows staged by TMA).
+//
+// Same contract as scan_kernel / scan_mma_kernel (scan.cuh): sim[q][d] = rows[d,:] . query[q,:] for the
+// gensim call sites webui.py:352 and webui.py:205, every stored row read from HBM once per launch, plus
+// the per-query maximum webui.py:377 needs.  Per tile the work is a [128 docs x 300] x [300 x 32 queries]
+// contraction; to stay at fp32-level accuracy (TF32 keeps 11 significant bits) both operands are split
+// hi + lo and three products are accumulated (3xTF32: hi*hi + hi*lo + lo*hi; lo*lo ~ 2^-22 relative is
+// dropped).
+//
+// Shared-memory bandwidth (128 B/clk/SM) is the scarce resource next to HBM: an SS-mode MMA re-reads its
+// 4 KB A slice from shared memory for every instruction, three times per k-step here, and a split pass
+// through shared memory reads and writes every element again (first version: 3.9 ms per launch, no pipe
+// saturated).  So the doc rows cross shared memory exactly once: TMA writes a box, a split warp reads it
+// into registers, and BOTH split images go to TMEM (tcgen05.st), from where the MMA takes its A operand;
+// only the 32 queries (B operand, 1 KB per instruction) are read from shared memory by the tensor core.
+//
+// Pipeline of one persistent CTA per SM (448 threads):
+//   warp 12  producer   one lane streams [128 rows x 32 k] boxes (16 KB) of the row matrix through a 2-D
+//                       tensor map with 128-byte swizzle into a 9-stage ring (144 KB in flight); the 10th
+//                       k-block is zero-filled by TMA beyond column 300, rows beyond n are zero-filled too.
+//   warps 4-11 split    warp w owns TMEM lanes 32*(w%4).. = 32 docs of the box (lane = doc; with the
+//                       128-byte swizzle the eight 16-B chunks of eight neighbouring rows sit in eight
+//                       distinct bank groups, so the row-wise LDS.128 are conflict-free); the two warps of
+//                       a lane quarter alternate over the k-blocks: x -> hi = rn_tf32(x), lo = rn_tf32(x - hi)
+//                       -> tcgen05.st into one of 4 A stages (64 TMEM columns each); the shared-memory stage
+//                       is released as soon as it has been read.
+//   warp 13  MMA        one lane issues 3 tcgen05.mma (M=128, N=32, K=8, A from TMEM) per k-step: hi*hi into
+//                       one of 3 K-range accumulators (the tensor core's accumulation rounds toward zero;
+//                       short chains keep that bias below fp32 rounding), hi*lo and lo*hi into a 4th; commits
+//                       release the A stages; accumulators double-buffered (2 x 128 columns).
+//   warps 0-3 epilogue  tcgen05.ld (lane = doc), fp32 sum of the 4 accumulators, coalesced stores of
+//                       sim[q][128 docs], running per-query maxima.
+// The queries arrive pre-split (split_queries_kernel) as [hi(32) | lo(32)][300] and are loaded once per CTA.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ais {
+
+constexpr int TC_M = 128;                       // docs per tile (UMMA M)
+constexpr int TC_N = 32;                        // queries per pass (UMMA N)
+constexpr int TC_KB = 32;                       // fp32 elements per k-block = 128 B = the swizzle span
+constexpr int TC_NKB = 10;                      // ceil(300 / 32); the last block carries 12 live columns
+constexpr int TC_A_BYTES = TC_M * 128;          // 16 KB per (stage)
+constexpr int TC_B_BYTES = TC_N * 128;          // 4 KB per (k-block, hi|lo)
+constexpr int TC_RAW_STAGES = 9;
+constexpr int TC_A_STAGES = 4;                  // A-operand stages in TMEM: [hi 32 columns | lo 32 columns] each
+constexpr int TC_MAIN = 3;                      // hi*hi accumulators per tile (K ranges)
+constexpr int TC_ACC_COLS = (TC_MAIN + 1) * TC_N;
+constexpr int TC_A_COL0 = 2 * TC_ACC_COLS;      // TMEM columns: [acc buffer 0 | acc buffer 1 | A stages]
+constexpr int TC_TMEM_COLS = 512;
+static_assert(TC_A_COL0 + TC_A_STAGES * 2 * TC_KB <= TC_TMEM_COLS, "TMEM budget");
+constexpr int TC_EPI_WARPS = 4, TC_SPLIT_WARPS = 8;
+constexpr int TC_PRODUCER_WARP = TC_EPI_WARPS + TC_SPLIT_WARPS, TC_MMA_WARP = TC_PRODUCER_WARP + 1;
+constexpr int TC_THREADS = 32 * (TC_MMA_WARP + 1);
+
+constexpr int TC_OFF_BHI = 0;
+constexpr int TC_OFF_BLO = TC_OFF_BHI + TC_NKB * TC_B_BYTES;
+constexpr int TC_OFF_RAW = TC_OFF_BLO + TC_NKB * TC_B_BYTES;
+constexpr int TC_OFF_BAR = TC_OFF_RAW + TC_RAW_STAGES * TC_A_BYTES;
+constexpr int TC_N_BARS = 2 * TC_RAW_STAGES + 2 * TC_A_STAGES + 2 + 2 + 1;
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + TC_N_BARS * 8 + 16 + 1024;   // + 1024: manual alignment of the base
+
+// UMMA instruction descriptor: D fp32 (bit 4), A/B TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// shared-memory matrix descriptor, K-major SWIZZLE_128B: stride between 8-row groups 1024 B, version 1 (Blackwell)
+constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
+    return ((uint64_t)TC_DESC_HI << 32) | (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | (1u << 16));
+}
+// D[tmem] (+)= A[tmem: lane = row, column = k] * B[smem descriptor]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_2d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// a wait that cannot hang the GPU: a protocol error traps instead of spinning forever
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, int tag) {
+    uint32_t spins = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFu) == 0) {
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ll) {
+                printf("scan_tc_kernel: barrier wait timed out (role %d, block %d)\n", tag, (int)blockIdx.x);
+                __trap();
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ float rn_tf32(float x) {          // round to nearest TF32 (11 significant bits), two integer ops
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+// queries [nq][300] -> qsplit [64][300]: rows 0..31 hi, rows 32..63 lo (zero rows beyond nq)
+__global__ void split_queries_kernel(const float* __restrict__ q, int nq, float* __restrict__ qsplit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TC_N * DIM) return;
+    const float v = (i / DIM) < nq ? q[i] : 0.0f;
+    const float hi = rn_tf32(v);
+    qsplit[i] = hi;
+    qsplit[TC_N * DIM + i] = rn_tf32(v - hi);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_q, int64_t n,
+               float* __restrict__ out, int64_t ld, uint32_t* __restrict__ max_keys, int nq_live) {
+    extern __shared__ unsigned char smem_unaligned[];
+    const uint32_t base = (smem_u32(smem_unaligned) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_unaligned + (base - smem_u32(smem_unaligned));
+    const uint32_t bar0 = base + TC_OFF_BAR;
+    const uint32_t full_raw = bar0, empty_raw = bar0 + 8 * TC_RAW_STAGES;
+    const uint32_t a_full = bar0 + 16 * TC_RAW_STAGES, a_empty = a_full + 8 * TC_A_STAGES;
+    const uint32_t acc_full = a_empty + 8 * TC_A_STAGES, acc_empty = acc_full + 16, b_full = acc_empty + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + TC_OFF_BAR + TC_N_BARS * 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_RAW_STAGES; ++s) {
+            mbar_init(full_raw + 8 * s, 1);
+            mbar_init(empty_raw + 8 * s, TC_SPLIT_WARPS / 2);
+        }
+        for (int s = 0; s < TC_A_STAGES; ++s) {
+            mbar_init(a_full + 8 * s, TC_SPLIT_WARPS / 2);
+            mbar_init(a_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + 8 * b, 1);
+            mbar_init(acc_empty + 8 * b, TC_EPI_WARPS);
+        }
+        mbar_init(b_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == TC_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + TC_OFF_BAR + TC_N_BARS * 8),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t n_tiles = (n + TC_M - 1) / TC_M;
+    const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int total_it = my_tiles * TC_NKB;
+
+    if (warp == TC_PRODUCER_WARP) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_rows)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_q)) : "memory");
+            mbar_arrive_expect_tx(b_full, 2 * TC_NKB * TC_B_BYTES);
+            for (int kb = 0; kb < TC_NKB; ++kb) {
+                tma_2d(base + TC_OFF_BHI + kb * TC_B_BYTES, &tm_q, kb * TC_KB, 0, b_full);
+                tma_2d(base + TC_OFF_BLO + kb * TC_B_BYTES, &tm_q, kb * TC_KB, TC_N, b_full);
+            }
+            int it = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int row0 = (int)(((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TC_M);
+                for (int kb = 0; kb < TC_NKB; ++kb, ++it) {
+                    const int s = it % TC_RAW_STAGES;
+                    mbar_wait_guarded(empty_raw + 8 * s, ((it / TC_RAW_STAGES) & 1) ^ 1, 0);
+                    mbar_arrive_expect_tx(full_raw + 8 * s, TC_A_BYTES);
+                    tma_2d(base + TC_OFF_RAW + s * TC_A_BYTES, &tm_rows, kb * TC_KB, row0, full_raw + 8 * s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == TC_MMA_WARP) {
+        // ---------------- MMA issuer ----------------
+        // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform registers);
+        // one elected lane issues.  At N = 32 an MMA occupies the tensor pipe for 16 clocks only, so the issue
+        // sequence itself must stay short: everything is unrolled and the descriptors advance by constants.
+        mbar_wait_guarded(b_full, 0, 1);
+        tc_fence_after();
+        const uint64_t b_hi0 = tc_desc(base + TC_OFF_BHI), b_lo0 = tc_desc(base + TC_OFF_BLO);
+        int it = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int buf = t & 1;
+            mbar_wait_guarded(acc_empty + 8 * buf, ((t >> 1) & 1) ^ 1, 2);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * TC_ACC_COLS;
+#pragma unroll
+            for (int kb = 0; kb < TC_NKB; ++kb, ++it) {
+                const int as = it % TC_A_STAGES;
+                mbar_wait_guarded(a_full + 8 * as, (it / TC_A_STAGES) & 1, 3);
+                tc_fence_after();
+                const int m = kb * TC_MAIN / TC_NKB;
+                const bool first_main = kb == 0 || ((kb - 1) * TC_MAIN / TC_NKB) != m;
+                const int nks = kb == TC_NKB - 1 ? 2 : 4;                  // 300 = 9*32 + 12 -> two k-steps of 8 in the last block
+                const uint32_t a_hi = tmem_base + TC_A_COL0 + as * 2 * TC_KB, a_lo = a_hi + TC_KB;
+                const uint64_t b_hi = b_hi0 + (uint64_t)(kb * (TC_B_BYTES >> 4)), b_lo = b_lo0 + (uint64_t)(kb * (TC_B_BYTES >> 4));
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (ks < nks) {
+                            // + 2: 32 B along K inside the swizzle span, in 16-B units
+                            tc_mma_ts(acc + m * TC_N, a_hi + ks * 8, b_hi + 2 * ks, (first_main && ks == 0) ? 0u : 1u);
+                            tc_mma_ts(acc + TC_MAIN * TC_N, a_hi + ks * 8, b_lo + 2 * ks, (kb == 0 && ks == 0) ? 0u : 1u);
+                            tc_mma_ts(acc + TC_MAIN * TC_N, a_lo + ks * 8, b_hi + 2 * ks, 1u);
+                        }
+                    }
+                    tc_commit(a_empty + 8 * as);
+                    if (kb == TC_NKB - 1) tc_commit(acc_full + 8 * buf);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= TC_EPI_WARPS) {
+        // ---------------- split warps: box -> registers -> hi | lo in TMEM ----------------
+        const int g = (warp - TC_EPI_WARPS) >> 2;                            // the two warps of a lane quarter take even / odd k-blocks
+        const int quarter = warp & 3;                                        // TMEM lanes this warp may touch: 32 * (warp % 4) ..
+        const int r = quarter * 32 + lane;                                   // row of the box = TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + TC_A_COL0;
+        for (int it = g; it < total_it; it += 2) {
+            const int s = it % TC_RAW_STAGES, as = it % TC_A_STAGES;
+            mbar_wait_guarded(full_raw + 8 * s, (it / TC_RAW_STAGES) & 1, 4);
+            const unsigned char* rowp = gbase + TC_OFF_RAW + s * TC_A_BYTES + r * 128;
+            float4 x[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float v[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float h = rn_tf32(v[j]);
+                    hi[4 * c + j] = __float_as_uint(h);
+                    lo[4 * c + j] = __float_as_uint(rn_tf32(v[j] - h));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_raw + 8 * s);                   // the box is in registers: refill the stage
+            mbar_wait_guarded(a_empty + 8 * as, ((it / TC_A_STAGES) & 1) ^ 1, 5);
+            tc_fence_after();
+            const uint32_t ta = lane_addr + as * 2 * TC_KB;
+            tc_st16(ta, reinterpret_cast<const uint32_t(&)[16]>(hi[0]));
+            tc_st16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(hi[16]));
+            tc_st16(ta + 32, reinterpret_cast<const uint32_t(&)[16]>(lo[0]));
+            tc_st16(ta + 48, reinterpret_cast<const uint32_t(&)[16]>(lo[16]));
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + 8 * as);
+        }
+    } else {
+        // ---------------- epilogue warps: TMEM -> registers -> sim[q][doc] ----------------
+        float lmax[TC_N];
+#pragma unroll
+        for (int q = 0; q < TC_N; ++q) lmax[q] = -INFINITY;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int buf = t & 1;
+            mbar_wait_guarded(acc_full + 8 * buf, (t >> 1) & 1, 6);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * TC_ACC_COLS;
+            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TC_M + warp * 32 + lane;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t a[TC_MAIN + 1][16];
+#pragma unroll
+                for (int m = 0; m <= TC_MAIN; ++m) tc_ld16(taddr + m * TC_N + half * 16, a[m]);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float v = __uint_as_float(a[0][j]);
+#pragma unroll
+                    for (int m = 1; m < TC_MAIN; ++m) v += __uint_as_float(a[m][j]);
+                    v += __uint_as_float(a[TC_MAIN][j]);
+                    const int q = half * 16 + j;
+                    if (row < n && q < nq_live) {
+                        out[(int64_t)q * ld + row] = v;
+                        lmax[q] = fmaxf(lmax[q], v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+        }
+#pragma unroll
+        for (int q = 0; q < TC_N; ++q) {
+            const float m = warp_max(lmax[q]);
+            if (lane == 0 && q < nq_live) atomicMax(&max_keys[q], fkey(m));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace ais
