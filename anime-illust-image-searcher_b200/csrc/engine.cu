@@ -163,9 +163,10 @@ struct ais_engine {
     int64_t scan_launches = 0, kernel_launches = 0, fullsort_fallbacks = 0, bytes_device = 0;
     bool profiling = false;
     bool use_mma = true;       // >= 5 queries per pass: tensor-core scan (3xTF32); AIS_SCAN_SIMT=1 keeps the fp32 SIMT kernel
+    bool tc_wide = true;       // > 32 queries left: 64 queries per tcgen05 pass (AIS_SCAN_TC_WIDE=0: 32)
     int tc_min = 17;           // >= tc_min queries left in a batch: tcgen05 scan, 32 queries per pass (AIS_SCAN_TC_MIN; 0 = off)
     Buf qsplit;                // [64][300] hi | lo images of the queries of one tcgen05 pass
-    CUtensorMap tm_rows, tm_q;
+    CUtensorMap tm_rows, tm_q[2];       // tm_q[0]: 32 queries per pass, tm_q[1]: 64
     const void* tm_rows_ptr = nullptr;  int64_t tm_rows_n = -1;  const void* tm_q_ptr = nullptr;
     double scan_ms_total = 0.0;
     std::vector<cudaEvent_t> ev_pending, ev_free;
@@ -384,11 +385,20 @@ int make_row_tmap(CUtensorMap* tm, const void* ptr, int64_t n_rows, int box_rows
     return AIS_OK;
 }
 
-int launch_scan_tc(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
+template <int N, int MAIN, int CROSS, int RAW, int ASTG, int NBUF>
+void launch_tc_variant(ais_engine* e, int grid, float* out, uint32_t* max_keys, int nq) {
+    scan_tc_kernel<N, MAIN, CROSS, RAW, ASTG, NBUF><<<grid, TC_THREADS, tc_smem_bytes(N, RAW), e->stream>>>(e->tm_rows, e->tm_q[N == 64], e->n_vec, out,
+                                                                                           e->ld, max_keys, nq);
+}
+
+// one tcgen05 pass over the rows for up to 32 (wide = false) or 64 (wide = true) queries
+int launch_scan_tc(ais_engine* e, const float* d_q, int nq, bool wide, float* out, uint32_t* max_keys) {
     if (e->n_vec >= (1LL << 31)) return fail(AIS_ERR_INVALID, "tcgen05 scan: shard larger than 2^31 docs");
-    TRY(dev_alloc(e, e->qsplit, (size_t)2 * TC_N * DIM * sizeof(float)));
+    const int n_pass = wide ? 64 : 32;
+    TRY(dev_alloc(e, e->qsplit, (size_t)2 * TC_N_MAX * DIM * sizeof(float)));
     if (e->tm_q_ptr != e->qsplit.p) {
-        TRY(make_row_tmap(&e->tm_q, e->qsplit.p, 2 * TC_N, TC_N));
+        TRY(make_row_tmap(&e->tm_q[0], e->qsplit.p, 2 * 32, 32));
+        TRY(make_row_tmap(&e->tm_q[1], e->qsplit.p, 2 * 64, 64));
         e->tm_q_ptr = e->qsplit.p;
     }
     if (e->tm_rows_ptr != e->rows.p || e->tm_rows_n != e->n_vec) {
@@ -396,7 +406,7 @@ int launch_scan_tc(ais_engine* e, const float* d_q, int nq, float* out, uint32_t
         e->tm_rows_ptr = e->rows.p;
         e->tm_rows_n = e->n_vec;
     }
-    split_queries_kernel<<<(TC_N * DIM + 255) / 256, 256, 0, e->stream>>>(d_q, nq, e->qsplit.as<float>());
+    split_queries_kernel<<<(n_pass * DIM + 255) / 256, 256, 0, e->stream>>>(d_q, nq, n_pass, e->qsplit.as<float>());
     LAUNCHED(e);
     const int64_t n_tiles = (e->n_vec + TC_M - 1) / TC_M;
     const int grid = (int)(n_tiles < e->sm_count ? n_tiles : e->sm_count);
@@ -408,7 +418,8 @@ int launch_scan_tc(ais_engine* e, const float* d_q, int nq, float* out, uint32_t
         }
         CK(cudaEventRecord(a, e->stream));
     }
-    scan_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, e->stream>>>(e->tm_rows, e->tm_q, e->n_vec, out, e->ld, max_keys, nq);
+    if (wide) launch_tc_variant<64, 2, 1, 4, 2, 2>(e, grid, out, max_keys, nq);
+    else launch_tc_variant<32, 3, 1, 6, 4, 2>(e, grid, out, max_keys, nq);
     LAUNCHED(e);
     e->scan_launches++;
     if (e->profiling) {
@@ -434,9 +445,10 @@ int launch_scan(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* m
     for (int q0 = 0; q0 < nq;) {
         const int left = nq - q0;
         const bool tc = e->tc_min > 0 && left >= e->tc_min;
-        const int cap = tc ? TC_N : MAX_QT;
+        const bool wide = tc && e->tc_wide && left > 32;
+        const int cap = tc ? (wide ? 64 : 32) : MAX_QT;
         const int m = left < cap ? left : cap;
-        if (tc) TRY(launch_scan_tc(e, d_q + (size_t)q0 * DIM, m, out + (size_t)q0 * e->ld, max_keys + q0));
+        if (tc) TRY(launch_scan_tc(e, d_q + (size_t)q0 * DIM, m, wide, out + (size_t)q0 * e->ld, max_keys + q0));
         else TRY(launch_scan_one(e, d_q + (size_t)q0 * DIM, m, out + (size_t)q0 * e->ld, max_keys + q0));
         q0 += m;
     }
@@ -451,7 +463,8 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<8>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
-    CK(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(scan_tc_kernel<32, 3, 1, 6, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(32, 6)));
+    CK(cudaFuncSetAttribute(scan_tc_kernel<64, 2, 1, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64, 4)));
     CK(cudaFuncSetAttribute(bm25_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(bm25_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
@@ -1052,6 +1065,7 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
     const char* simt = getenv("AIS_SCAN_SIMT");
     e->use_mma = !(simt && simt[0] == '1');
     if (const char* tcm = getenv("AIS_SCAN_TC_MIN")) e->tc_min = atoi(tcm);
+    if (const char* tcw = getenv("AIS_SCAN_TC_WIDE")) e->tc_wide = atoi(tcw) != 0;
     int s = set_scan_attrs();
     if (s != AIS_OK) { cudaStreamDestroy(e->own_stream); delete e; return s; }
     *out = e;

@@ -40,31 +40,24 @@
 namespace ais {
 
 constexpr int TC_M = 128;                       // docs per tile (UMMA M)
-constexpr int TC_N = 32;                        // queries per pass (UMMA N)
+constexpr int TC_N_MAX = 64;                    // queries per pass (UMMA N): 32 or 64
 constexpr int TC_KB = 32;                       // fp32 elements per k-block = 128 B = the swizzle span
 constexpr int TC_NKB = 10;                      // ceil(300 / 32); the last block carries 12 live columns
 constexpr int TC_A_BYTES = TC_M * 128;          // 16 KB per (stage)
-constexpr int TC_B_BYTES = TC_N * 128;          // 4 KB per (k-block, hi|lo)
-constexpr int TC_RAW_STAGES = 9;
-constexpr int TC_A_STAGES = 4;                  // A-operand stages in TMEM: [hi 32 columns | lo 32 columns] each
-constexpr int TC_MAIN = 3;                      // hi*hi accumulators per tile (K ranges)
-constexpr int TC_ACC_COLS = (TC_MAIN + 1) * TC_N;
-constexpr int TC_A_COL0 = 2 * TC_ACC_COLS;      // TMEM columns: [acc buffer 0 | acc buffer 1 | A stages]
 constexpr int TC_TMEM_COLS = 512;
-static_assert(TC_A_COL0 + TC_A_STAGES * 2 * TC_KB <= TC_TMEM_COLS, "TMEM budget");
 constexpr int TC_EPI_WARPS = 4, TC_SPLIT_WARPS = 8;
 constexpr int TC_PRODUCER_WARP = TC_EPI_WARPS + TC_SPLIT_WARPS, TC_MMA_WARP = TC_PRODUCER_WARP + 1;
 constexpr int TC_THREADS = 32 * (TC_MMA_WARP + 1);
 
-constexpr int TC_OFF_BHI = 0;
-constexpr int TC_OFF_BLO = TC_OFF_BHI + TC_NKB * TC_B_BYTES;
-constexpr int TC_OFF_RAW = TC_OFF_BLO + TC_NKB * TC_B_BYTES;
-constexpr int TC_OFF_BAR = TC_OFF_RAW + TC_RAW_STAGES * TC_A_BYTES;
-constexpr int TC_N_BARS = 2 * TC_RAW_STAGES + 2 * TC_A_STAGES + 2 + 2 + 1;
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + TC_N_BARS * 8 + 16 + 1024;   // + 1024: manual alignment of the base
+// shared memory: [B hi: 10 k-blocks x N rows x 128 B | B lo | landing ring | barriers | TMEM base]
+constexpr int tc_smem_bytes(int n_q, int raw_stages) {                 // + 1024: manual alignment of the base
+    return 2 * TC_NKB * n_q * 128 + raw_stages * TC_A_BYTES + (2 * raw_stages + 2 * 8 + 2 + 2 + 1) * 8 + 16 + 1024;
+}
 
 // UMMA instruction descriptor: D fp32 (bit 4), A/B TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t tc_idesc(int n_q) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_q >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
 // shared-memory matrix descriptor, K-major SWIZZLE_128B: stride between 8-row groups 1024 B, version 1 (Blackwell)
 constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 
@@ -72,12 +65,12 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
     return ((uint64_t)TC_DESC_HI << 32) | (uint64_t)(((smem_addr >> 4) & 0x3FFFu) | (1u << 16));
 }
 // D[tmem] (+)= A[tmem: lane = row, column = k] * B[smem descriptor]
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -113,6 +106,12 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // a wait that cannot hang the GPU: a protocol error traps instead of spinning forever
@@ -141,19 +140,42 @@ __device__ __forceinline__ float rn_tf32(float x) {          // round to nearest
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
-// queries [nq][300] -> qsplit [64][300]: rows 0..31 hi, rows 32..63 lo (zero rows beyond nq)
-__global__ void split_queries_kernel(const float* __restrict__ q, int nq, float* __restrict__ qsplit) {
+// queries [nq][300] -> qsplit [2 * n_pass][300]: rows 0..n_pass-1 hi, then n_pass rows lo (zero rows beyond nq)
+__global__ void split_queries_kernel(const float* __restrict__ q, int nq, int n_pass, float* __restrict__ qsplit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= TC_N * DIM) return;
+    if (i >= n_pass * DIM) return;
     const float v = (i / DIM) < nq ? q[i] : 0.0f;
     const float hi = rn_tf32(v);
     qsplit[i] = hi;
-    qsplit[TC_N * DIM + i] = rn_tf32(v - hi);
+    qsplit[n_pass * DIM + i] = rn_tf32(v - hi);
 }
 
+// TC_N: queries per pass; TC_MAIN: hi*hi accumulators (the k-steps rotate over them); TC_CROSS: accumulators of the
+// cross terms; TC_RAW_STAGES: depth of the shared-memory landing ring; TC_A_STAGES: A-operand stages in TMEM
+// ([hi 32 columns | lo 32 columns] each); TC_NBUF: accumulator buffers (2: the epilogue of a tile overlaps the MMAs
+// of the next one).  Measured on B200, 10 M docs (profiles/r01_d):
+//   N = 32: <32,3,1,6,4,2>: 4 accumulators x 32 columns x 2 buffers = 256 columns + 4 A stages; 80 KB of queries,
+//           6 x 16 KB ring: 2.10 ms per pass = 12.0 GB read + 1.28 GB written at 6.3 TB/s (0.97 of the copy peak).
+//   N = 64: <64,2,1,4,2,2>: 3 accumulators x 64 columns x 2 buffers = 384 columns + 2 A stages; 160 KB of queries,
+//           4 x 16 KB ring: 2.67 ms per pass (5.45 TB/s of total traffic).
+// What did NOT matter (each tried): ring depth 4/6/9, 2 vs 4 vs 5 A stages, rotating vs K-range accumulators, one vs
+// two accumulator buffers at equal instruction count.  What did: the MMA issue sequence (unrolled, uniform registers:
+// 3.8 -> 2.2 ms) and the instruction count of the split and epilogue warps, which share four issue slots.
+template <int TC_N, int TC_MAIN, int TC_CROSS, int TC_RAW_STAGES, int TC_A_STAGES, int TC_NBUF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_q, int64_t n,
                float* __restrict__ out, int64_t ld, uint32_t* __restrict__ max_keys, int nq_live) {
+    constexpr int TC_NACC = TC_MAIN + TC_CROSS;
+    constexpr int TC_ACC_COLS = TC_NACC * TC_N;
+    static_assert(TC_CROSS == 1 || TC_CROSS == 2 || TC_CROSS == 4, "cross accumulators");
+    constexpr int TC_A_COL0 = TC_NBUF * TC_ACC_COLS;   // TMEM columns: [acc buffer(s) | A stages]
+    static_assert(TC_A_COL0 + TC_A_STAGES * 2 * TC_KB <= TC_TMEM_COLS, "TMEM budget");
+    static_assert(TC_A_STAGES <= 8 && (TC_NBUF == 1 || TC_NBUF == 2), "barrier slots");
+    constexpr int TC_B_BYTES = TC_N * 128;          // one k-block of the hi (or lo) query image
+    constexpr uint32_t TC_IDESC = tc_idesc(TC_N);
+    constexpr int TC_OFF_BHI = 0, TC_OFF_BLO = TC_NKB * TC_B_BYTES, TC_OFF_RAW = 2 * TC_NKB * TC_B_BYTES;
+    constexpr int TC_OFF_BAR = TC_OFF_RAW + TC_RAW_STAGES * TC_A_BYTES;
+    constexpr int TC_N_BARS = 2 * TC_RAW_STAGES + 2 * TC_A_STAGES + 2 + 2 + 1;
     extern __shared__ unsigned char smem_unaligned[];
     const uint32_t base = (smem_u32(smem_unaligned) + 1023u) & ~1023u;
     unsigned char* gbase = smem_unaligned + (base - smem_u32(smem_unaligned));
@@ -174,7 +196,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
             mbar_init(a_full + 8 * s, TC_SPLIT_WARPS / 2);
             mbar_init(a_empty + 8 * s, 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < TC_NBUF; ++b) {
             mbar_init(acc_full + 8 * b, 1);
             mbar_init(acc_empty + 8 * b, TC_EPI_WARPS);
         }
@@ -228,8 +250,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
         const uint64_t b_hi0 = tc_desc(base + TC_OFF_BHI), b_lo0 = tc_desc(base + TC_OFF_BLO);
         int it = 0;
         for (int t = 0; t < my_tiles; ++t) {
-            const int buf = t & 1;
-            mbar_wait_guarded(acc_empty + 8 * buf, ((t >> 1) & 1) ^ 1, 2);
+            const int buf = t % TC_NBUF;
+            mbar_wait_guarded(acc_empty + 8 * buf, ((t / TC_NBUF) & 1) ^ 1, 2);
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * TC_ACC_COLS;
 #pragma unroll
@@ -237,8 +259,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
                 const int as = it % TC_A_STAGES;
                 mbar_wait_guarded(a_full + 8 * as, (it / TC_A_STAGES) & 1, 3);
                 tc_fence_after();
-                const int m = kb * TC_MAIN / TC_NKB;
-                const bool first_main = kb == 0 || ((kb - 1) * TC_MAIN / TC_NKB) != m;
                 const int nks = kb == TC_NKB - 1 ? 2 : 4;                  // 300 = 9*32 + 12 -> two k-steps of 8 in the last block
                 const uint32_t a_hi = tmem_base + TC_A_COL0 + as * 2 * TC_KB, a_lo = a_hi + TC_KB;
                 const uint64_t b_hi = b_hi0 + (uint64_t)(kb * (TC_B_BYTES >> 4)), b_lo = b_lo0 + (uint64_t)(kb * (TC_B_BYTES >> 4));
@@ -246,10 +266,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         if (ks < nks) {
+                            // Accumulators rotate with the k-step: an MMA that accumulates into the tile the previous
+                            // MMA wrote waits out the tensor pipe's latency (~100 clocks at N = 32, six times its own
+                            // duration), so consecutive MMAs target different TMEM tiles.
+                            const int g = kb * 4 + ks;                                  // k-step of the tile, 0..37
+                            const int cm = g % TC_MAIN;
+                            const int ca = TC_MAIN + (TC_CROSS == 4 ? (g & 1) * 2 : 0);
+                            const int cb = TC_CROSS == 1 ? ca : ca + 1;
+                            const bool first_c = g < (TC_CROSS == 4 ? 2 : 1);
                             // + 2: 32 B along K inside the swizzle span, in 16-B units
-                            tc_mma_ts(acc + m * TC_N, a_hi + ks * 8, b_hi + 2 * ks, (first_main && ks == 0) ? 0u : 1u);
-                            tc_mma_ts(acc + TC_MAIN * TC_N, a_hi + ks * 8, b_lo + 2 * ks, (kb == 0 && ks == 0) ? 0u : 1u);
-                            tc_mma_ts(acc + TC_MAIN * TC_N, a_lo + ks * 8, b_hi + 2 * ks, 1u);
+                            tc_mma_ts(acc + cm * TC_N, a_hi + ks * 8, b_hi + 2 * ks, TC_IDESC, g < TC_MAIN ? 0u : 1u);
+                            tc_mma_ts(acc + ca * TC_N, a_hi + ks * 8, b_lo + 2 * ks, TC_IDESC, first_c ? 0u : 1u);
+                            tc_mma_ts(acc + cb * TC_N, a_lo + ks * 8, b_hi + 2 * ks, TC_IDESC, (first_c && TC_CROSS != 1) ? 0u : 1u);
                         }
                     }
                     tc_commit(a_empty + 8 * as);
@@ -277,9 +305,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
                 const float v[4] = {x[c].x, x[c].y, x[c].z, x[c].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                    // hi = RN_tf32(x) (two integer ops); lo = x - hi exactly (<= 13 significant bits), which the tensor
+                    // core truncates to TF32 itself: |error| <= 2^-21 |x|, sign-symmetric.  Three instructions per element:
+                    // the split warps share their issue slots with the epilogue, and every instruction here counts.
                     const float h = rn_tf32(v[j]);
                     hi[4 * c + j] = __float_as_uint(h);
-                    lo[4 * c + j] = __float_as_uint(rn_tf32(v[j] - h));
+                    lo[4 * c + j] = __float_as_uint(v[j] - h);
                 }
             }
             __syncwarp();
@@ -298,37 +329,52 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
         }
     } else {
         // ---------------- epilogue warps: TMEM -> registers -> sim[q][doc] ----------------
+        // Lane = doc.  Per (doc, query): the fp32 sum of the accumulators, one coalesced store (a warp writes 128
+        // contiguous bytes of sim[q]) and one FMNMX into the lane's running maximum of that query; the lanes'
+        // maxima meet once, at the end.  Queries beyond nq_live are zero vectors: their columns are stored too
+        // (the work array is padded to the pass width) and simply never read.
         float lmax[TC_N];
 #pragma unroll
         for (int q = 0; q < TC_N; ++q) lmax[q] = -INFINITY;
+        constexpr int CH = TC_N > 32 ? 8 : 16;                               // columns per TMEM load: register budget
         for (int t = 0; t < my_tiles; ++t) {
-            const int buf = t & 1;
-            mbar_wait_guarded(acc_full + 8 * buf, (t >> 1) & 1, 6);
+            const int buf = t % TC_NBUF;
+            mbar_wait_guarded(acc_full + 8 * buf, (t / TC_NBUF) & 1, 6);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * TC_ACC_COLS;
             const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TC_M + warp * 32 + lane;
+            const bool live = row < n;
+            float* orow = out + row;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t a[TC_MAIN + 1][16];
+            for (int c = 0; c < TC_N / CH; ++c) {
+                uint32_t a[TC_NACC][CH];
 #pragma unroll
-                for (int m = 0; m <= TC_MAIN; ++m) tc_ld16(taddr + m * TC_N + half * 16, a[m]);
+                for (int m = 0; m < TC_NACC; ++m) {
+                    if constexpr (CH == 16) tc_ld16(taddr + m * TC_N + c * CH, a[m]);
+                    else tc_ld8(taddr + m * TC_N + c * CH, a[m]);
+                }
                 tc_wait_ld();
+                if (c == TC_N / CH - 1) {                                    // the tile is out of TMEM: hand the buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+                }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float v = __uint_as_float(a[0][j]);
+                for (int j = 0; j < CH; ++j) {
+                    float x = __uint_as_float(a[0][j]);
 #pragma unroll
-                    for (int m = 1; m < TC_MAIN; ++m) v += __uint_as_float(a[m][j]);
-                    v += __uint_as_float(a[TC_MAIN][j]);
-                    const int q = half * 16 + j;
-                    if (row < n && q < nq_live) {
-                        out[(int64_t)q * ld + row] = v;
+                    for (int m = 1; m < TC_MAIN; ++m) x += __uint_as_float(a[m][j]);
+                    float y = __uint_as_float(a[TC_MAIN][j]);
+#pragma unroll
+                    for (int m = TC_MAIN + 1; m < TC_NACC; ++m) y += __uint_as_float(a[m][j]);
+                    const float v = x + y;                                   // the hi*hi sums, then the small cross terms
+                    const int q = c * CH + j;
+                    if (live) {
+                        orow[(int64_t)q * ld] = v;
                         lmax[q] = fmaxf(lmax[q], v);
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
         }
 #pragma unroll
         for (int q = 0; q < TC_N; ++q) {

@@ -96,7 +96,8 @@ def test_fresh_index_vs_oracle(n_docs, vocab, tf_frac):
 
 def test_batched_queries_equal_single_queries():
     """<= 4 queries per pass run the same fp32 SIMT scan (bit-equal results for any batching); >= 5 queries per
-    pass run the tensor-core scan (3xTF32, fp32-level accuracy): same ranking within the score tolerance."""
+    pass run a tensor-core scan (3xTF32, fp32-level accuracy; mma.sync up to 16, tcgen05 beyond): same ranking within
+    the score tolerance."""
     from gpu_util import same_ranking
     idx = synth.generate_index(40000, vocab_size=2000, seed=77)
     queries = synth.generate_queries(idx, 37, seed=3)
@@ -105,7 +106,7 @@ def test_batched_queries_equal_single_queries():
     qs = [Q.make_query(q, t2i, infer) for q in queries]
     single = E.SearchEngine.from_index(idx, max_batch=1)
     ref = single.search_raw(qs, 100, E.PRF_STORED_ROWS)
-    for mb in (2, 3, 4, 8, 13, 16, 37):
+    for mb in (2, 3, 4, 8, 13, 16, 29, 37):
         eng = E.SearchEngine.from_index(idx, max_batch=mb)
         got = eng.search_raw(qs, 100, E.PRF_STORED_ROWS)
         assert np.array_equal(got[3], ref[3])
@@ -124,25 +125,31 @@ def test_batched_queries_equal_single_queries():
         eng.close()
 
 
-def test_tensor_core_scan_accuracy():
-    """index[vec] through the batched (mma.sync 3xTF32) scan against the fp64 dot product: fp32-level error."""
-    idx = synth.generate_index(20000, vocab_size=500, seed=12)
-    rng = np.random.default_rng(4)
-    for mb in (8, 16):
-        eng = E.SearchEngine.from_index(idx, max_batch=mb)
-        vecs = rng.standard_normal((mb, 300)).astype(np.float32)
-        vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
-        qs = [E.Query(v, np.array([0], np.int32), np.array([1.0])) for v in vecs]
-        # stage_score leaves the dense scores in the engine; read them back through the combined-score seam
-        import torch
-        maxes = torch.empty((mb, 2), dtype=torch.float64, device="cuda")
-        eng.stage_score(qs, maxes)
-        torch.cuda.synchronize()
-        eng.synchronize()
-        want_max = (idx.rows.astype(np.float64) @ vecs.T.astype(np.float64)).max(axis=0)
-        got_max = maxes.cpu().numpy()[:, 1]
-        assert np.abs(got_max - want_max).max() <= 2e-6 * np.abs(want_max).max()
-        eng.close()
+@pytest.mark.parametrize("mb", [8, 16, 24, 32, 47, 64, 100])
+def test_tensor_core_scan_accuracy(mb):
+    """index[vec] through the batched scans against the fp64 dot product, every doc of every query: fp32-level error.
+    8/16: mma.sync 3xTF32 (scan.cuh); 17..32: tcgen05 32 queries per pass; > 32: tcgen05 64 per pass (scan_tc.cuh).
+    The bound is what numpy's own fp32 dot product (the reference's arithmetic) stays within, too."""
+    import torch
+    n_docs = 128 * 148 + 77                                   # ragged last tile, more tiles than CTAs
+    idx = synth.generate_index(n_docs, vocab_size=500, seed=12)
+    rng = np.random.default_rng(4 + mb)
+    eng = E.SearchEngine.from_index(idx, max_batch=mb)
+    vecs = rng.standard_normal((mb, 300)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    qs = [E.Query(v, np.array([0], np.int32), np.array([1.0])) for v in vecs]
+    maxes = torch.empty((mb, 2), dtype=torch.float64, device="cuda")
+    eng.stage_score(qs, maxes)
+    torch.cuda.synchronize()
+    eng.synchronize()
+    want = idx.rows.astype(np.float64) @ vecs.T.astype(np.float64)          # [n][mb]
+    scale = np.abs(want).max(axis=0)
+    got_max = maxes.cpu().numpy()[:, 1]
+    assert np.abs(got_max - want.max(axis=0)).max() <= 2e-6 * scale.max()
+    for q in range(mb):
+        got = eng.debug_read("sim", q)
+        assert np.abs(got - want[:, q]).max() <= 2e-6 * scale[q], (mb, q)
+    eng.close()
 
 
 def test_constants_are_honoured_at_call_time():
