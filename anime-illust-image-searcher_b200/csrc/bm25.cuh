@@ -67,6 +67,7 @@ struct Bm25Args {
     // phase 1: normalise + combine with the dot scores (webui.py:376-383), store the combined scores, segment maxima
     const float* sim; double* fin; const double* maxes; double wb; float wd;
     uint64_t* seg_max; int seg_mod;                            // seg_max[q][sub % seg_mod]
+    uint64_t* tile_max; int64_t tile_ld;                       // tile_max[q][sub]: best key of the sub-tile (the collect pass skips by it)
 };
 
 // One WARP per (sub-tile of BM25_SUB docs, query), no block barriers: every warp runs its own dependency chain
@@ -264,6 +265,7 @@ bm25_warp_kernel(Bm25Args A) {
         }
         best = any ? dkey(fbest) : KEY_EMPTY;
         best = warp_max_u64(best);
+        if (lane == 0) A.tile_max[(int64_t)qi * A.tile_ld + sub] = best;
         if (lane == 0 && best != KEY_EMPTY)
             atomicMax(reinterpret_cast<unsigned long long*>(&A.seg_max[(size_t)qi * 2048 + (int)(sub % A.seg_mod)]),
                       (unsigned long long)best);
@@ -280,6 +282,7 @@ bm25_warp_kernel(Bm25Args A) {
         best = k > best ? k : best;
     }
     best = warp_max_u64(best);
+    if (lane == 0) A.tile_max[(int64_t)qi * A.tile_ld + sub] = best;
     if (lane == 0 && best != KEY_EMPTY)
         atomicMax(reinterpret_cast<unsigned long long*>(&A.seg_max[(size_t)qi * 2048 + (int)(sub % A.seg_mod)]),
                   (unsigned long long)best);

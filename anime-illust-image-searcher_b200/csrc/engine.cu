@@ -29,6 +29,7 @@
 #include "select2.cuh"
 
 using namespace ais;
+static_assert(SEL_TILE == BM25_SUB, "the BM25 sub-tile is the tile of the tile-maximum table");
 
 namespace {
 
@@ -148,6 +149,7 @@ struct ais_engine {
     Buf fs_keys, fs_ids, fs_count;
     Buf bm25_slices;
     int bm25_t_cap = 1;
+    Buf tile_max;  int64_t tile_ld = 0;       // [qt_cap][tile_ld] best key per 256-doc tile (select2.cuh)
     Buf seg_max, sel_thr, surv_count, surv_keys, surv_ids, gate, witness, last_keys, wit_table;
     uint64_t* h_last_keys = nullptr;
     int sel_k_cap = 0, out_topn_cap = 0;
@@ -164,7 +166,7 @@ struct ais_engine {
     bool profiling = false;
     bool use_mma = true;       // >= 5 queries per pass: tensor-core scan (3xTF32); AIS_SCAN_SIMT=1 keeps the fp32 SIMT kernel
     bool tc_wide = true;       // > 32 queries left: 64 queries per tcgen05 pass (AIS_SCAN_TC_WIDE=0: 32)
-    int tc_min = 17;           // >= tc_min queries left in a batch: tcgen05 scan, 32 queries per pass (AIS_SCAN_TC_MIN; 0 = off)
+    int tc_min = 9;            // >= tc_min queries left in a batch: tcgen05 scan, 32 or 64 queries per pass (AIS_SCAN_TC_MIN; 0 = off)
     Buf qsplit;                // [64][300] hi | lo images of the queries of one tcgen05 pass
     CUtensorMap tm_rows, tm_q[2];       // tm_q[0]: 32 queries per pass, tm_q[1]: 64
     const void* tm_rows_ptr = nullptr;  int64_t tm_rows_n = -1;  const void* tm_q_ptr = nullptr;
@@ -241,6 +243,9 @@ int ensure_work(ais_engine* e) {
     TRY(dev_alloc(e, e->out_count, (size_t)q * sizeof(int32_t)));
     TRY(dev_alloc(e, e->out_amb, (size_t)q * sizeof(int32_t)));
     TRY(dev_alloc(e, e->seg_max, (size_t)q * SEG_MAX * sizeof(uint64_t)));
+    const int64_t tl = (l + SEL_TILE - 1) / SEL_TILE;
+    TRY(dev_alloc(e, e->tile_max, (size_t)q * tl * sizeof(uint64_t)));
+    e->tile_ld = tl;
     TRY(dev_alloc(e, e->sel_thr, (size_t)q * sizeof(uint64_t)));
     TRY(dev_alloc(e, e->surv_count, (size_t)q * sizeof(int)));
     TRY(dev_alloc(e, e->surv_keys, (size_t)q * SURV_CAP * sizeof(uint64_t)));
@@ -551,6 +556,8 @@ int launch_bm25_combine(ais_engine* e, int nq, const double* d_maxes, int* n_seg
     a.wd = (float)e->p.doc2vec_weight;
     a.seg_max = e->seg_max.as<uint64_t>();
     a.seg_mod = (int)segs;
+    a.tile_max = e->tile_max.as<uint64_t>();
+    a.tile_ld = e->tile_ld;
     bm25_warp_kernel<1><<<dim3((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq), BM25_THREADS, BM25_SMEM, e->stream>>>(a);
     LAUNCHED(e);
     return AIS_OK;
@@ -596,10 +603,14 @@ int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, 
     a.seeds_all = e->top_ids.as<int64_t>();
     a.depth = e->p.prf_depth;
     a.mode = mode;
-    int64_t S = (n + 31) / 32;
-    if (S > SEG_MAX) S = SEG_MAX;
+    // segments = groups of whole tiles (modes 1, 2; the BM25 kernel of mode 0 interleaves its sub-tiles over the segments)
+    a.n_tiles = (n + SEL_TILE - 1) / SEL_TILE;
+    const int64_t tiles_per_seg = a.n_tiles > 0 ? (a.n_tiles + SEG_MAX - 1) / SEG_MAX : 1;
+    const int64_t S = (a.n_tiles + tiles_per_seg - 1) / tiles_per_seg;
     a.n_seg = (int)S;
-    a.seg_len = S > 0 ? (n + S - 1) / S : 0;
+    a.seg_len = tiles_per_seg * SEL_TILE;
+    a.tile_max = e->tile_max.as<uint64_t>();
+    a.tile_ld = e->tile_ld;
     a.seg_max = e->seg_max.as<uint64_t>();
     a.max_all = mode == 2 ? e->maxr_key.as<uint64_t>() : nullptr;
     a.thr = e->sel_thr.as<uint64_t>();
@@ -619,8 +630,8 @@ int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, 
     threshold_kernel<<<nq, 256, 0, e->stream>>>(a.seg_max, a.n_seg, k, a.thr, a.surv_count, a.gate);
     LAUNCHED(e);
     if (n > 0) {
-        int64_t cb = (n + COLLECT_THREADS * 8 - 1) / (COLLECT_THREADS * 8);
-        if (cb > 8LL * e->sm_count) cb = 8LL * e->sm_count;
+        int64_t cb = (a.n_tiles + COLLECT_THREADS - 1) / COLLECT_THREADS;     // one lane per tile
+        if (cb > 2LL * e->sm_count) cb = 2LL * e->sm_count;
         const dim3 g3((unsigned)cb, (unsigned)nq);
         if (mode == 2) collect_kernel<2><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
         else collect_kernel<1><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
@@ -1080,7 +1091,7 @@ int ais_destroy(ais_engine* e) {
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
-                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->sel_thr, &e->surv_count,
+                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->tile_max, &e->sel_thr, &e->surv_count,
                    &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices, &e->qsplit})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,

@@ -6,8 +6,11 @@
 //   2. threshold: T = k-th largest segment maximum.  At least k docs (one per such segment) have
 //                 key >= T, so the global top-k is contained in {key >= T}; with docs spread over the
 //                 segments |{key >= T}| ~ -S ln(1 - k/S), i.e. barely more than k.
-//   3. collect:   stream again, append every doc with key >= T to a survivor list (warp-aggregated
-//                 atomics), then ONE block sorts the survivors (key desc, doc id asc) and writes the top-k.
+//   3. collect:   passes 1 also record the best key of every 256-doc tile; the collect pass reads those
+//                 (8 B per 256 docs) and visits only tiles whose best key reaches T - a few hundred of the
+//                 39 063 tiles of a 10 M-doc shard - appending every doc with key >= T to a survivor list
+//                 (warp-aggregated atomics); then ONE block sorts the survivors (key desc, doc id asc) and
+//                 writes the top-k.
 // If the survivors exceed SURV_CAP (top docs clustered in few segments) the query's gate flag is raised
 // and the buffer-based kernels of select.cuh, launched right behind and gated on that flag, redo it.
 //
@@ -25,6 +28,7 @@ constexpr int SEG_WARPS = 8;             // warps (= segments) per block
 constexpr int SEG_MIN_DOCS = 64;
 constexpr int SURV_CAP = 4096;
 constexpr int COLLECT_THREADS = 256;
+constexpr int SEL_TILE = 256;            // docs per tile of the tile-maximum table (= BM25_SUB)
 
 // ---- score functors: key of doc i, false if the doc is not a candidate ---------------------------
 struct ScoreFinal {        // stored combined scores
@@ -57,8 +61,10 @@ struct SelectArgs {        // everything the three kernels share
     const int64_t* seeds_all;   // [nq][MAX_DEPTH] (mode 2)
     int depth;
     int mode;                   // 0 combine (pass 1), 1 stored finals, 2 rerank blend (pass 2)
-    int n_seg; int64_t seg_len;
+    int n_seg; int64_t seg_len; // a segment = seg_len / SEL_TILE whole tiles
     uint64_t* seg_max;          // [nq][SEG_MAX]
+    uint64_t* tile_max;         // [nq][tile_ld]: best key of every SEL_TILE docs, seeds included (an upper bound: skip filter only)
+    int64_t tile_ld, n_tiles;
     uint64_t* max_all;          // [nq] atomicMax over ALL docs (mode 2: max R) or null
     uint64_t* thr;              // [nq]
     int* surv_count;            // [nq]
@@ -78,7 +84,15 @@ __device__ __forceinline__ void with_functor(const SelectArgs& a, int qi, const 
     }
 }
 
-// ---- 1. segment maxima -----------------------------------------------------------------------------
+// 64-bit warp maximum with two redux.sync instead of five shuffle rounds
+__device__ __forceinline__ uint64_t warp_max_u64_redux(uint64_t v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((uint64_t)mh << 32) | ml;
+}
+
+// ---- 1. segment maxima (+ tile maxima) ---------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(32 * SEG_WARPS)
 segmax_kernel(SelectArgs a) {
@@ -92,40 +106,50 @@ segmax_kernel(SelectArgs a) {
     const int seg = blockIdx.x * SEG_WARPS + warp;
     uint64_t best = KEY_EMPTY, all_best = KEY_EMPTY;
     if (seg < a.n_seg) {
-        const int64_t lo = (int64_t)seg * a.seg_len;
-        const int64_t hi = lo + a.seg_len < a.n ? lo + a.seg_len : a.n;
+        const int64_t tiles_per_seg = a.seg_len / SEL_TILE;
+        const int64_t t0 = (int64_t)seg * tiles_per_seg;
+        const int64_t t1 = t0 + tiles_per_seg < a.n_tiles ? t0 + tiles_per_seg : a.n_tiles;
+        uint64_t* tmax = a.tile_max + (int64_t)qi * a.tile_ld;
         with_functor<MODE>(a, qi, seeds, [&](auto& f) {
-            int64_t i = lo + lane;
 #pragma unroll 1
-            for (; i + 96 < hi; i += 128) {
-                uint64_t k0, k1, k2, k3;
-                f(i, a.id_base + i, k0);
-                f(i + 32, a.id_base + i + 32, k1);
-                f(i + 64, a.id_base + i + 64, k2);
-                f(i + 96, a.id_base + i + 96, k3);
-                const uint64_t m01 = k0 > k1 ? k0 : k1, m23 = k2 > k3 ? k2 : k3;
-                const uint64_t m = m01 > m23 ? m01 : m23;
-                all_best = m > all_best ? m : all_best;
-                if (m > best) {                       // rare after the first few iterations
-                    if (k0 > best && !f.is_seed(a.id_base + i)) best = k0;
-                    if (k1 > best && !f.is_seed(a.id_base + i + 32)) best = k1;
-                    if (k2 > best && !f.is_seed(a.id_base + i + 64)) best = k2;
-                    if (k3 > best && !f.is_seed(a.id_base + i + 96)) best = k3;
+            for (int64_t tile = t0; tile < t1; ++tile) {
+                const int64_t lo = tile * SEL_TILE;
+                const int64_t hi = lo + SEL_TILE < a.n ? lo + SEL_TILE : a.n;
+                uint64_t tbest = KEY_EMPTY;
+                int64_t i = lo + lane;
+#pragma unroll 1
+                for (; i + 96 < hi; i += 128) {
+                    uint64_t k0, k1, k2, k3;
+                    f(i, a.id_base + i, k0);
+                    f(i + 32, a.id_base + i + 32, k1);
+                    f(i + 64, a.id_base + i + 64, k2);
+                    f(i + 96, a.id_base + i + 96, k3);
+                    const uint64_t m01 = k0 > k1 ? k0 : k1, m23 = k2 > k3 ? k2 : k3;
+                    const uint64_t m = m01 > m23 ? m01 : m23;
+                    tbest = m > tbest ? m : tbest;
+                    if (m > best) {                       // rare after the first few iterations
+                        if (k0 > best && !f.is_seed(a.id_base + i)) best = k0;
+                        if (k1 > best && !f.is_seed(a.id_base + i + 32)) best = k1;
+                        if (k2 > best && !f.is_seed(a.id_base + i + 64)) best = k2;
+                        if (k3 > best && !f.is_seed(a.id_base + i + 96)) best = k3;
+                    }
                 }
-            }
-            for (; i < hi; i += 32) {
-                uint64_t k;
-                f(i, a.id_base + i, k);
-                all_best = k > all_best ? k : all_best;
-                if (k > best && !f.is_seed(a.id_base + i)) best = k;
+                for (; i < hi; i += 32) {
+                    uint64_t k;
+                    f(i, a.id_base + i, k);
+                    tbest = k > tbest ? k : tbest;
+                    if (k > best && !f.is_seed(a.id_base + i)) best = k;
+                }
+                tbest = warp_max_u64_redux(tbest);
+                if (lane == 0) tmax[tile] = tbest;
+                all_best = tbest > all_best ? tbest : all_best;
             }
         });
         best = warp_max_u64(best);
         if (lane == 0) a.seg_max[(size_t)qi * SEG_MAX + seg] = best;
     }
     if (a.max_all) {
-        all_best = warp_max_u64(all_best);
-        if (lane == 0) wall[warp] = all_best;
+        if (lane == 0) wall[warp] = all_best;              // already warp-uniform
         __syncthreads();
         if (threadIdx.x == 0) {
             uint64_t m = wall[0];
@@ -166,6 +190,7 @@ threshold_kernel(const uint64_t* __restrict__ seg_max, int n_seg, int k, uint64_
 }
 
 // ---- 3a. collect the survivors -------------------------------------------------------------------------
+// One lane per tile reads the tile's best key; the warp then walks the (rare) tiles that reach the threshold.
 template <int MODE>
 __global__ void __launch_bounds__(COLLECT_THREADS)
 collect_kernel(SelectArgs a) {
@@ -179,35 +204,33 @@ collect_kernel(SelectArgs a) {
     int* cnt = a.surv_count + qi;
     uint64_t* sk = a.surv_keys + (size_t)qi * SURV_CAP;
     int64_t* si = a.surv_ids + (size_t)qi * SURV_CAP;
-    const int64_t stride = (int64_t)gridDim.x * COLLECT_THREADS;
-    const int64_t n_round = ((a.n + 31) / 32) * 32;          // whole warps stay together for the ballots
+    const uint64_t* tmax = a.tile_max + (int64_t)qi * a.tile_ld;
+    const int64_t warp_id = ((int64_t)blockIdx.x * COLLECT_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * COLLECT_THREADS) >> 5;
     with_functor<MODE>(a, qi, seeds, [&](auto& f) {
-        for (int64_t i0 = (int64_t)blockIdx.x * COLLECT_THREADS + threadIdx.x; i0 < n_round; i0 += 4 * stride) {
-            uint64_t key[4];
-            bool pass[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                         // four independent loads in flight per thread
-                const int64_t i = i0 + u * stride;
-                key[u] = KEY_EMPTY;
-                if (i < a.n) f(i, a.id_base + i, key[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t i = i0 + u * stride;
-                pass[u] = i < a.n && key[u] >= T && !f.is_seed(a.id_base + i);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (i0 + u * stride >= n_round) break;            // warp-uniform
-                const unsigned m = __ballot_sync(0xffffffffu, pass[u]);
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    int base = 0;
-                    if (lane == leader) base = atomicAdd(cnt, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (pass[u]) {
-                        const int pos = base + __popc(m & ((1u << lane) - 1u));
-                        if (pos < SURV_CAP) { sk[pos] = key[u]; si[pos] = a.id_base + i0 + u * stride; }
+        for (int64_t tb = warp_id * 32; tb < a.n_tiles; tb += n_warps * 32) {
+            const int64_t my_tile = tb + lane;
+            unsigned todo = __ballot_sync(0xffffffffu, my_tile < a.n_tiles && tmax[my_tile] >= T);
+            while (todo) {
+                const int b = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t lo = (tb + b) * SEL_TILE;
+#pragma unroll 1
+                for (int u = 0; u < SEL_TILE / 32; ++u) {
+                    const int64_t i = lo + u * 32 + lane;
+                    uint64_t key = KEY_EMPTY;
+                    if (i < a.n) f(i, a.id_base + i, key);
+                    const bool pass = i < a.n && key >= T && !f.is_seed(a.id_base + i);
+                    const unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (m) {
+                        const int leader = __ffs(m) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(cnt, __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (pass) {
+                            const int pos = base + __popc(m & ((1u << lane) - 1u));
+                            if (pos < SURV_CAP) { sk[pos] = key; si[pos] = a.id_base + i; }
+                        }
                     }
                 }
             }
