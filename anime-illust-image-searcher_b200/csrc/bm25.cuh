@@ -19,7 +19,7 @@ constexpr int BM25_SUB = 256;                    // docs per warp-private sub-ti
 constexpr int BM25_WARPS = 8;                    // warps (= consecutive sub-tiles of one query) per block
 constexpr int BM25_THREADS = 32 * BM25_WARPS;
 constexpr int BM25_STAGE = 256;                  // staged postings per (sub-tile, query); denser slices take the direct path
-constexpr int BM25_WARP_SMEM = BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8 + 4 * BM25_SUB;
+constexpr int BM25_WARP_SMEM = BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8 + 3 * BM25_SUB;
 constexpr int BM25_SMEM = BM25_WARPS * BM25_WARP_SMEM;
 
 struct QueryTerms {  // device-resident, one per query of the pass
@@ -62,22 +62,38 @@ struct Bm25Args {
     const int32_t* post_doc; const int32_t* post_tf;          // post_tf may be null: tf == 1
     const double* idf; const double* kd; int64_t n; int32_t n_vocab;
     const QueryTerms* queries; double magic, k1p1;
-    // phase 0: per-query maximum (+ optional dense scores for the compute_bm25_scores seam)
+    // phase 0: per-query maximum + the sub-tile's record (+ optional dense scores for the compute_bm25_scores seam)
     uint64_t* max_keys; double* dense_out; int64_t ld;
+    uint32_t* tile_hdr;                                        // [q][tile_ld][8]: bitmap of the docs whose BM25 value is not the default
     // phase 1: normalise + combine with the dot scores (webui.py:376-383), store the combined scores, segment maxima
     const float* sim; double* fin; const double* maxes; double wb; float wd;
     uint64_t* seg_max; int seg_mod;                            // seg_max[q][sub % seg_mod]
     uint64_t* tile_max; int64_t tile_ld;                       // tile_max[q][sub]: best key of the sub-tile (the collect pass skips by it)
 };
 
-// One WARP per (sub-tile of BM25_SUB docs, query), no block barriers: every warp runs its own dependency chain
-// (slice bounds -> postings -> K_d -> fp64 contribution -> ordered accumulation -> epilogue), so an SM overlaps
-// ~40 of them.  The postings of ALL the query's terms that fall into the sub-tile are first staged in the warp's
-// shared memory with their contributions (independent global loads), then summed term by term, in the query's
-// term order (fp64 addition is not associative; webui.py:139-170 adds term by term), out of shared memory only.
-template <int PHASE>
+// number of required terms of a query (weight > magic; webui.py:161 - 1000 itself is NOT required)
+__device__ __forceinline__ int count_required(const QueryTerms& Q, double magic, int lane) {
+    int n_required = 0;
+    for (int j0 = 0; j0 < Q.n_terms; j0 += 32) {
+        const int j = j0 + lane;
+        n_required += __popc(__ballot_sync(0xffffffffu, j < Q.n_terms && Q.weight[j] > magic));
+    }
+    return n_required;
+}
+
+// Phase 0.  One WARP per (sub-tile of BM25_SUB docs, query), no block barriers: every warp runs its own dependency chain
+// (slice bounds -> postings -> K_d -> fp64 contribution -> ordered accumulation -> record), so an SM overlaps ~40 of
+// them.  The postings of ALL the query's terms that fall into the sub-tile are first staged in the warp's shared memory
+// with their contributions (independent global loads), then summed term by term, in the query's term order (fp64
+// addition is not associative; webui.py:139-170 adds term by term), out of shared memory only.
+//
+// Result: the per-query maximum (webui.py:379 needs it before anything can be combined) and the sub-tile's RECORD -
+// a 256-bit map of the docs whose BM25 value differs from the default of the query (0, or -inf when the query has a
+// required term) in tile_hdr, and those values, compacted in doc order, in the first slots of the sub-tile's own range
+// of the combined-score array `fin` (which phase 1 of the same warp position overwrites with the final scores).  Phase 1
+// therefore never touches posting lists, K_d or an fp64 division per posting again.
 __global__ void __launch_bounds__(BM25_THREADS)
-bm25_warp_kernel(Bm25Args A) {
+bm25_score_kernel(Bm25Args A) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t sub = (int64_t)blockIdx.x * BM25_WARPS + warp;
@@ -90,7 +106,6 @@ bm25_warp_kernel(Bm25Args A) {
     uint8_t* excl = base + BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8;
     uint8_t* reqc = excl + BM25_SUB;
     uint8_t* st_doc = reqc + BM25_SUB;
-    uint8_t* need = st_doc + BM25_SUB;
 
     const int qi = blockIdx.y;
     const QueryTerms& Q = A.queries[qi];
@@ -98,6 +113,7 @@ bm25_warp_kernel(Bm25Args A) {
     const int64_t lo = sub * BM25_SUB;
     const int64_t hi = (lo + BM25_SUB < A.n) ? lo + BM25_SUB : A.n;
     const int64_t* sl = A.slices + (int64_t)qi * A.t_cap * (A.n_sub + 1) + sub;
+    uint32_t* hdr = A.tile_hdr + ((int64_t)qi * A.tile_ld + sub) * 8;
 
     // slice bounds of every term, exclusive prefix sum of their lengths, number of required terms
     int n_required = 0, carry = 0;
@@ -124,163 +140,186 @@ bm25_warp_kernel(Bm25Args A) {
     if (lane == 0) off[0] = 0;
     const int E = carry;
     __syncwarp();
-
-    if (E > 0) {
-        for (int i = lane; i < BM25_SUB; i += 32) { acc[i] = 0.0; excl[i] = 0; reqc[i] = 0; }
-        __syncwarp();
-        if (E <= BM25_STAGE) {
-            // ---- stage every posting of the sub-tile with its contribution (all global loads independent) ----
-            for (int e = lane; e < E; e += 32) {
-                int j = 0;
-                while (e >= off[j + 1]) ++j;
-                const int64_t p = sl_a[j] + (e - off[j]);
-                const int d = A.post_doc[p];
-                const double w = Q.weight[j];
-                double c = 0.0;
-                if (!(w < 0.0)) {
-                    const int t = Q.term[j];
-                    const double mult = (w > A.magic) ? (w - A.magic) : w;
-                    const double idfv = (t >= 0 && t < A.n_vocab) ? A.idf[t] : 0.0;
-                    const double tf = A.post_tf ? (double)A.post_tf[p] : 1.0;
-                    const double denom = __dadd_rn(tf, A.kd[d]);                       // webui.py:145
-                    const double numer = __dmul_rn(tf, A.k1p1);                        // webui.py:146
-                    const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));     // webui.py:147
-                    c = __dmul_rn(mult, score);                                        // webui.py:167,170
-                }
-                st_doc[e] = (uint8_t)(d - lo);
-                st_val[e] = c;
-            }
-            __syncwarp();
-            // ---- ordered accumulation, shared memory only (doc ids are unique inside a term) ----
-            for (int j = 0; j < T; ++j) {
-                const double w = Q.weight[j];
-                const bool required = w > A.magic;
-                for (int e = off[j] + lane; e < off[j + 1]; e += 32) {
-                    const int l = st_doc[e];
-                    if (w < 0.0) excl[l] = 1;                                          // webui.py:154-160
-                    else {
-                        acc[l] = __dadd_rn(acc[l], st_val[e]);
-                        if (required) reqc[l] = (uint8_t)(reqc[l] + 1);
-                    }
-                }
-                __syncwarp();
-            }
-        } else {
-            // ---- direct path for very dense sub-tiles ----
-            for (int j = 0; j < T; ++j) {
-                const double w = Q.weight[j];
-                const int t = Q.term[j];
-                const int64_t a = sl_a[j], b = a + (off[j + 1] - off[j]);
-                if (w < 0.0) {
-                    for (int64_t p = a + lane; p < b; p += 32) excl[A.post_doc[p] - lo] = 1;
-                } else {
-                    const bool required = w > A.magic;
-                    const double mult = required ? (w - A.magic) : w;
-                    const double idfv = (t >= 0 && t < A.n_vocab) ? A.idf[t] : 0.0;
-                    for (int64_t p = a + lane; p < b; p += 32) {
-                        const int d = A.post_doc[p];
-                        const double tf = A.post_tf ? (double)A.post_tf[p] : 1.0;
-                        const double denom = __dadd_rn(tf, A.kd[d]);
-                        const double numer = __dmul_rn(tf, A.k1p1);
-                        const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));
-                        const int l = (int)(d - lo);
-                        acc[l] = __dadd_rn(acc[l], __dmul_rn(mult, score));
-                        if (required) reqc[l] = (uint8_t)(reqc[l] + 1);
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    }
-    // a sub-tile no term touches: every doc scores +0.0, or -inf when the query has a required term
+    // a doc no term touches scores +0.0, or -inf when the query has a required term (webui.py:160,168)
     const double untouched = n_required > 0 ? -INFINITY : 0.0;
 
-    // webui.py:160,168: excluded hit, or a required term missing -> -inf (absorbing under +=)
-    if (PHASE == 0) {
-        if (E == 0 && !A.dense_out) {
-            // every doc of the sub-tile scores `untouched`; one relaxed check instead of 256 identical keys
-            const uint64_t k = dkey(untouched);
-            if (lane == 0 && k > *(volatile uint64_t*)&A.max_keys[qi])
-                atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)k);
-            return;
+    if (E == 0) {
+        if (lane < 8) hdr[lane] = 0u;
+        if (A.dense_out)
+            for (int64_t d = lo + lane; d < hi; d += 32) A.dense_out[(int64_t)qi * A.ld + d] = untouched;
+        const uint64_t k = dkey(untouched);              // one relaxed check instead of 256 identical keys
+        if (lane == 0 && k > *(volatile uint64_t*)&A.max_keys[qi])
+            atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)k);
+        return;
+    }
+
+    for (int i = lane; i < BM25_SUB; i += 32) { acc[i] = 0.0; excl[i] = 0; reqc[i] = 0; }
+    __syncwarp();
+    if (E <= BM25_STAGE) {
+        // ---- stage every posting of the sub-tile with its contribution (all global loads independent) ----
+        for (int e = lane; e < E; e += 32) {
+            int j = 0;
+            while (e >= off[j + 1]) ++j;
+            const int64_t p = sl_a[j] + (e - off[j]);
+            const int d = A.post_doc[p];
+            const double w = Q.weight[j];
+            double c = 0.0;
+            if (!(w < 0.0)) {
+                const int t = Q.term[j];
+                const double mult = (w > A.magic) ? (w - A.magic) : w;
+                const double idfv = (t >= 0 && t < A.n_vocab) ? A.idf[t] : 0.0;
+                const double tf = A.post_tf ? (double)A.post_tf[p] : 1.0;
+                const double denom = __dadd_rn(tf, A.kd[d]);                       // webui.py:145
+                const double numer = __dmul_rn(tf, A.k1p1);                        // webui.py:146
+                const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));     // webui.py:147
+                c = __dmul_rn(mult, score);                                        // webui.py:167,170
+            }
+            st_doc[e] = (uint8_t)(d - lo);
+            st_val[e] = c;
         }
-        uint64_t best = dkey(-INFINITY);
-        for (int64_t d = lo + lane; d < hi; d += 32) {
-            const int l = (int)(d - lo);
-            const double v = E > 0 ? ((excl[l] || reqc[l] != n_required) ? -INFINITY : acc[l]) : untouched;
-            if (A.dense_out) A.dense_out[(int64_t)qi * A.ld + d] = v;
+        __syncwarp();
+        // ---- ordered accumulation, shared memory only (doc ids are unique inside a term) ----
+        for (int j = 0; j < T; ++j) {
+            const double w = Q.weight[j];
+            const bool required = w > A.magic;
+            for (int e = off[j] + lane; e < off[j + 1]; e += 32) {
+                const int l = st_doc[e];
+                if (w < 0.0) excl[l] = 1;                                          // webui.py:154-160
+                else {
+                    acc[l] = __dadd_rn(acc[l], st_val[e]);
+                    if (required) reqc[l] = (uint8_t)(reqc[l] + 1);
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- direct path for very dense sub-tiles ----
+        for (int j = 0; j < T; ++j) {
+            const double w = Q.weight[j];
+            const int t = Q.term[j];
+            const int64_t a = sl_a[j], b = a + (off[j + 1] - off[j]);
+            if (w < 0.0) {
+                for (int64_t p = a + lane; p < b; p += 32) excl[A.post_doc[p] - lo] = 1;
+            } else {
+                const bool required = w > A.magic;
+                const double mult = required ? (w - A.magic) : w;
+                const double idfv = (t >= 0 && t < A.n_vocab) ? A.idf[t] : 0.0;
+                for (int64_t p = a + lane; p < b; p += 32) {
+                    const int d = A.post_doc[p];
+                    const double tf = A.post_tf ? (double)A.post_tf[p] : 1.0;
+                    const double denom = __dadd_rn(tf, A.kd[d]);
+                    const double numer = __dmul_rn(tf, A.k1p1);
+                    const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));
+                    const int l = (int)(d - lo);
+                    acc[l] = __dadd_rn(acc[l], __dmul_rn(mult, score));
+                    if (required) reqc[l] = (uint8_t)(reqc[l] + 1);
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- record: bitmap + compacted values (doc order), and the maximum over the sub-tile ----
+    // webui.py:160,168: excluded hit, or a required term missing -> -inf (absorbing under +=)
+    double* rec = A.fin + (int64_t)qi * A.ld + lo;
+    uint64_t best = KEY_EMPTY;
+    int n_rec = 0;
+#pragma unroll
+    for (int u = 0; u < BM25_SUB / 32; ++u) {
+        const int l = u * 32 + lane;
+        const bool in = lo + l < hi;
+        const double v = (excl[l] || reqc[l] != n_required) ? -INFINITY : acc[l];
+        if (A.dense_out && in) A.dense_out[(int64_t)qi * A.ld + lo + l] = v;
+        const bool rec_it = in && v != untouched;                 // NaN never appears: idf, K_d and the weights are finite
+        const unsigned m = __ballot_sync(0xffffffffu, rec_it);
+        if (lane == 0) hdr[u] = m;
+        if (rec_it) {
+            rec[n_rec + __popc(m & ((1u << lane) - 1u))] = v;
             const uint64_t k = dkey(v);
             best = k > best ? k : best;
         }
-        best = warp_max_u64(best);
-        if (lane == 0 && best > *(volatile uint64_t*)&A.max_keys[qi])
-            atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)best);
-        return;
+        n_rec += __popc(m);
     }
-
-    // ---- phase 1: bm25 / max (the docs that carry a contribution are compacted first so that the fp64 division
-    //      runs with full warps), then 0.5*bm25n + 0.5*simn ----
-    const double maxb = A.maxes[2 * qi];
-    const float maxs = (float)A.maxes[2 * qi + 1];
-    if (E > 0 && maxb > 0.0) {
-        int nn = 0;
-        for (int i = lane; i < BM25_SUB; i += 32) {
-            const bool nd = acc[i] != 0.0 && !excl[i] && reqc[i] == n_required;
-            const unsigned m = __ballot_sync(0xffffffffu, nd);
-            if (nd) need[nn + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
-            nn += __popc(m);
-        }
-        __syncwarp();
-        for (int i = lane; i < nn; i += 32) {
-            const int l = need[i];
-            acc[l] = __ddiv_rn(acc[l], maxb);                                     // webui.py:379-380
-        }
-        __syncwarp();
-    }
-    uint64_t best = KEY_EMPTY;
-    const float* simq = A.sim + (int64_t)qi * A.ld;
-    double* finq = A.fin + (int64_t)qi * A.ld;
-    if (E == 0) {
-        // untouched sub-tile: bm25n is the same for all its docs (0 / max = 0, -inf / max = -inf)
-        const double wbb = __dmul_rn(A.wb, untouched);
-        float sv[BM25_SUB / 32];
-#pragma unroll
-        for (int u = 0; u < BM25_SUB / 32; ++u) {
-            const int64_t d = lo + u * 32 + lane;
-            sv[u] = d < hi ? __ldcs(simq + d) : 0.0f;
-        }
-        double fbest = -INFINITY;
-        bool any = false;
-#pragma unroll
-        for (int u = 0; u < BM25_SUB / 32; ++u) {
-            const int64_t d = lo + u * 32 + lane;
-            if (d < hi) {
-                float sn = sv[u];
-                if (maxs > 0.0f) sn = __fdiv_rn(sn, maxs);
-                const double f = __dadd_rn(wbb, (double)__fmul_rn(A.wd, sn));
-                __stcs(finq + d, f);
-                fbest = any ? fmax(fbest, f) : f;          // no NaNs on this path unless the rows hold them
-                any = true;
-            }
-        }
-        best = any ? dkey(fbest) : KEY_EMPTY;
-        best = warp_max_u64(best);
-        if (lane == 0) A.tile_max[(int64_t)qi * A.tile_ld + sub] = best;
-        if (lane == 0 && best != KEY_EMPTY)
-            atomicMax(reinterpret_cast<unsigned long long*>(&A.seg_max[(size_t)qi * 2048 + (int)(sub % A.seg_mod)]),
-                      (unsigned long long)best);
-        return;
-    }
-    for (int64_t d = lo + lane; d < hi; d += 32) {
-        const int l = (int)(d - lo);
-        const double b = (excl[l] || reqc[l] != n_required) ? -INFINITY : acc[l];
-        float s = __ldcs(simq + d);
-        if (maxs > 0.0f) s = __fdiv_rn(s, maxs);                                   // webui.py:377-378 (fp32 / fp32)
-        const double f = __dadd_rn(__dmul_rn(A.wb, b), (double)__fmul_rn(A.wd, s));   // webui.py:383
-        __stcs(finq + d, f);
-        const uint64_t k = dkey(f);
+    if (n_rec < (int)(hi - lo)) {                                 // some doc keeps the default
+        const uint64_t k = dkey(untouched);
         best = k > best ? k : best;
     }
+    best = warp_max_u64(best);
+    if (lane == 0 && best > *(volatile uint64_t*)&A.max_keys[qi])
+        atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)best);
+}
+
+constexpr int BM25C_WARPS = 8;
+constexpr int BM25C_THREADS = 32 * BM25C_WARPS;
+
+// Phase 1 (after the global maxima are known).  One warp per (sub-tile, query) again: read the record phase 0 left
+// (32-byte bitmap + compacted values), bm25 / max for the recorded docs (full warps on the fp64 division), then per
+// doc  final = wb * bm25n + wd * (sim / max sim)  (webui.py:376-383; fp32 / fp32, the products and the sum in the
+// reference's precisions), store it, and keep the sub-tile's best key for the select.
+__global__ void __launch_bounds__(BM25C_THREADS)
+bm25_combine_kernel(Bm25Args A) {
+    __shared__ double vals_all[BM25C_WARPS][BM25_SUB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t sub = (int64_t)blockIdx.x * BM25C_WARPS + warp;
+    if (sub >= A.n_sub) return;
+    double* vals = vals_all[warp];
+    const int qi = blockIdx.y;
+    const int64_t lo = sub * BM25_SUB;
+    const int64_t hi = (lo + BM25_SUB < A.n) ? lo + BM25_SUB : A.n;
+    const double maxb = A.maxes[2 * qi];
+    const float maxs = (float)A.maxes[2 * qi + 1];
+    const float* simq = A.sim + (int64_t)qi * A.ld;
+    double* finq = A.fin + (int64_t)qi * A.ld;
+
+    // every lane holds the whole bitmap (two broadcast 16-byte loads)
+    const uint4* hp = reinterpret_cast<const uint4*>(A.tile_hdr + ((int64_t)qi * A.tile_ld + sub) * 8);
+    const uint4 h0 = hp[0], h1 = hp[1];
+    const uint32_t w[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    int n_rec = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) n_rec += __popc(w[u]);
+
+    const int n_required = count_required(A.queries[qi], A.magic, lane);
+    double dflt = n_required > 0 ? -INFINITY : 0.0;               // bm25n of a doc without a record: 0 / max = 0, -inf / max = -inf
+    if (n_rec > 0) {
+        for (int i = lane; i < n_rec; i += 32) {
+            double v = finq[lo + i];
+            if (maxb > 0.0) v = __ddiv_rn(v, maxb);                                // webui.py:379-380
+            vals[i] = v;
+        }
+        __syncwarp();
+    }
+    const double wb_dflt = __dmul_rn(A.wb, dflt);
+
+    // the dot scores of the sub-tile first (independent loads), then the arithmetic
+    float sv[BM25_SUB / 32];
+#pragma unroll
+    for (int u = 0; u < BM25_SUB / 32; ++u) {
+        const int64_t d = lo + u * 32 + lane;
+        sv[u] = d < hi ? __ldcs(simq + d) : 0.0f;
+    }
+    double fbest = -INFINITY;
+    bool any = false, nan_seen = false;
+    int prefix = 0;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int u = 0; u < BM25_SUB / 32; ++u) {
+        const int64_t d = lo + u * 32 + lane;
+        double wbb = wb_dflt;
+        if ((w[u] >> lane) & 1u) wbb = __dmul_rn(A.wb, vals[prefix + __popc(w[u] & lt)]);
+        prefix += __popc(w[u]);
+        if (d < hi) {
+            float sn = sv[u];
+            if (maxs > 0.0f) sn = __fdiv_rn(sn, maxs);                             // webui.py:377-378 (fp32 / fp32)
+            const double f = __dadd_rn(wbb, (double)__fmul_rn(A.wd, sn));          // webui.py:383
+            __stcs(finq + d, f);
+            nan_seen = nan_seen || (f != f);
+            fbest = any ? fmax(fbest, f) : f;
+            any = true;
+        }
+    }
+    uint64_t best = any ? dkey(fbest) : KEY_EMPTY;
+    if (nan_seen) best = 0xFFF8000000000000ull;                    // a NaN score (e.g. weight 0 x -inf) sorts first, as dkey(NaN) does
     best = warp_max_u64(best);
     if (lane == 0) A.tile_max[(int64_t)qi * A.tile_ld + sub] = best;
     if (lane == 0 && best != KEY_EMPTY)

@@ -149,6 +149,7 @@ struct ais_engine {
     Buf fs_keys, fs_ids, fs_count;
     Buf bm25_slices;
     int bm25_t_cap = 1;
+    Buf tile_hdr;              // [qt_cap][tile_ld][8] bitmap of the docs with a BM25 record (bm25.cuh)
     Buf tile_max;  int64_t tile_ld = 0;       // [qt_cap][tile_ld] best key per 256-doc tile (select2.cuh)
     Buf seg_max, sel_thr, surv_count, surv_keys, surv_ids, gate, witness, last_keys, wit_table;
     uint64_t* h_last_keys = nullptr;
@@ -245,6 +246,7 @@ int ensure_work(ais_engine* e) {
     TRY(dev_alloc(e, e->seg_max, (size_t)q * SEG_MAX * sizeof(uint64_t)));
     const int64_t tl = (l + SEL_TILE - 1) / SEL_TILE;
     TRY(dev_alloc(e, e->tile_max, (size_t)q * tl * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->tile_hdr, (size_t)q * tl * 8 * sizeof(uint32_t)));
     e->tile_ld = tl;
     TRY(dev_alloc(e, e->sel_thr, (size_t)q * sizeof(uint64_t)));
     TRY(dev_alloc(e, e->surv_count, (size_t)q * sizeof(int)));
@@ -470,8 +472,7 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(scan_tc_kernel<32, 3, 1, 6, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(32, 6)));
     CK(cudaFuncSetAttribute(scan_tc_kernel<64, 2, 1, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64, 4)));
-    CK(cudaFuncSetAttribute(bm25_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
-    CK(cudaFuncSetAttribute(bm25_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
+    CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
     return AIS_OK;
 }
@@ -516,6 +517,9 @@ Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
     a.magic = e->p.require_magic;
     a.k1p1 = e->p.k1 + 1.0;
     a.ld = e->ld;
+    a.fin = e->fin.as<double>();
+    a.tile_hdr = e->tile_hdr.as<uint32_t>();
+    a.tile_ld = e->tile_ld;
     return a;
 }
 
@@ -534,7 +538,7 @@ int launch_bm25_max(ais_engine* e, int nq, double* dense_out) {
     Bm25Args a = bm25_args(e, n_sub);
     a.max_keys = e->maxb_key.as<uint64_t>();
     a.dense_out = dense_out;
-    bm25_warp_kernel<0><<<dim3((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq), BM25_THREADS, BM25_SMEM, e->stream>>>(a);
+    bm25_score_kernel<<<dim3((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq), BM25_THREADS, BM25_SMEM, e->stream>>>(a);
     LAUNCHED(e);
     return AIS_OK;
 }
@@ -558,7 +562,7 @@ int launch_bm25_combine(ais_engine* e, int nq, const double* d_maxes, int* n_seg
     a.seg_mod = (int)segs;
     a.tile_max = e->tile_max.as<uint64_t>();
     a.tile_ld = e->tile_ld;
-    bm25_warp_kernel<1><<<dim3((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq), BM25_THREADS, BM25_SMEM, e->stream>>>(a);
+    bm25_combine_kernel<<<dim3((unsigned)((n_sub + BM25C_WARPS - 1) / BM25C_WARPS), (unsigned)nq), BM25C_THREADS, 0, e->stream>>>(a);
     LAUNCHED(e);
     return AIS_OK;
 }
@@ -1091,7 +1095,7 @@ int ais_destroy(ais_engine* e) {
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
-                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->tile_max, &e->sel_thr, &e->surv_count,
+                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->tile_max, &e->tile_hdr, &e->sel_thr, &e->surv_count,
                    &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices, &e->qsplit})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,

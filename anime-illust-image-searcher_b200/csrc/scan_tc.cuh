@@ -331,12 +331,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
         // ---------------- epilogue warps: TMEM -> registers -> sim[q][doc] ----------------
         // Lane = doc.  Per (doc, query): the fp32 sum of the accumulators, one coalesced store (a warp writes 128
         // contiguous bytes of sim[q]) and one FMNMX into the lane's running maximum of that query; the lanes'
-        // maxima meet once, at the end.  Queries beyond nq_live are zero vectors: their columns are stored too
-        // (the work array is padded to the pass width) and simply never read.
+        // maxima meet once, at the end.  Column chunks beyond the live queries of the pass are skipped (never loaded,
+        // never stored); inside the last live chunk the zero-vector padding columns are stored too - the work arrays
+        // hold a multiple of 16 rows.
         float lmax[TC_N];
 #pragma unroll
         for (int q = 0; q < TC_N; ++q) lmax[q] = -INFINITY;
         constexpr int CH = TC_N > 32 ? 8 : 16;                               // columns per TMEM load: register budget
+        const int n_chunks = (nq_live + CH - 1) / CH;                        // >= 1
         for (int t = 0; t < my_tiles; ++t) {
             const int buf = t % TC_NBUF;
             mbar_wait_guarded(acc_full + 8 * buf, (t / TC_NBUF) & 1, 6);
@@ -347,6 +349,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
             float* orow = out + row;
 #pragma unroll
             for (int c = 0; c < TC_N / CH; ++c) {
+                if (c >= n_chunks) break;                                    // warp-uniform
                 uint32_t a[TC_NACC][CH];
 #pragma unroll
                 for (int m = 0; m < TC_NACC; ++m) {
@@ -354,7 +357,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
                     else tc_ld8(taddr + m * TC_N + c * CH, a[m]);
                 }
                 tc_wait_ld();
-                if (c == TC_N / CH - 1) {                                    // the tile is out of TMEM: hand the buffer back
+                if (c == n_chunks - 1) {                                     // the tile is out of TMEM: hand the buffer back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
