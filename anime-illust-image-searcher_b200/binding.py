@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libais_b200.so")
+LIB_PATH = os.environ.get("AIS_B200_LIB") or os.path.join(_HERE, "libais_b200.so")   # override: instrumented debug builds
 
 AIS_OK = 0
 AIS_ERR_INVALID, AIS_ERR_CUDA, AIS_ERR_NOT_LOADED, AIS_ERR_UNSUPPORTED, AIS_ERR_CALLBACK = 1, 2, 3, 4, 5

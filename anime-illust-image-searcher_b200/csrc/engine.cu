@@ -392,9 +392,9 @@ int make_row_tmap(CUtensorMap* tm, const void* ptr, int64_t n_rows, int box_rows
     return AIS_OK;
 }
 
-template <int N, int MAIN, int CROSS, int RAW, int ASTG, int NBUF>
+template <int N, int MAIN, int CROSS, int RAW, int ASTG, int ASUB, int NBUF>
 void launch_tc_variant(ais_engine* e, int grid, float* out, uint32_t* max_keys, int nq) {
-    scan_tc_kernel<N, MAIN, CROSS, RAW, ASTG, NBUF><<<grid, TC_THREADS, tc_smem_bytes(N, RAW), e->stream>>>(e->tm_rows, e->tm_q[N == 64], e->n_vec, out,
+    scan_tc_kernel<N, MAIN, CROSS, RAW, ASTG, ASUB, NBUF><<<grid, TC_THREADS, tc_smem_bytes(N, RAW), e->stream>>>(e->tm_rows, e->tm_q[N == 64], e->n_vec, out,
                                                                                            e->ld, max_keys, nq);
 }
 
@@ -425,8 +425,8 @@ int launch_scan_tc(ais_engine* e, const float* d_q, int nq, bool wide, float* ou
         }
         CK(cudaEventRecord(a, e->stream));
     }
-    if (wide) launch_tc_variant<64, 2, 1, 4, 2, 2>(e, grid, out, max_keys, nq);
-    else launch_tc_variant<32, 3, 1, 6, 4, 2>(e, grid, out, max_keys, nq);
+    if (wide) launch_tc_variant<64, 2, 1, 4, 2, 1, 2>(e, grid, out, max_keys, nq);
+    else launch_tc_variant<32, 3, 1, 6, 4, 1, 2>(e, grid, out, max_keys, nq);
     LAUNCHED(e);
     e->scan_launches++;
     if (e->profiling) {
@@ -470,8 +470,8 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<8>()));
     CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
-    CK(cudaFuncSetAttribute(scan_tc_kernel<32, 3, 1, 6, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(32, 6)));
-    CK(cudaFuncSetAttribute(scan_tc_kernel<64, 2, 1, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64, 4)));
+    CK(cudaFuncSetAttribute(scan_tc_kernel<32, 3, 1, 6, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(32, 6)));
+    CK(cudaFuncSetAttribute(scan_tc_kernel<64, 2, 1, 4, 2, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64, 4)));
     CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
     return AIS_OK;
@@ -1528,6 +1528,15 @@ int ais_debug_read(ais_engine* e, int32_t which, int32_t query, void* out) {
     CK(cudaStreamSynchronize(e->stream));
     return AIS_OK;
 }
+
+#ifdef AIS_TC_TRACE
+extern "C" int ais_debug_tc_trace(ais_engine* e, long long* out /*[4][256][4]*/) {
+    DeviceGuard g(e->device);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 4 * 256 * 4));
+    return AIS_OK;
+}
+#endif
 
 // ---- introspection ----------------------------------------------------------------------------------------
 int ais_set_profiling(ais_engine* e, int on) {

@@ -45,7 +45,7 @@ constexpr int TC_KB = 32;                       // fp32 elements per k-block = 1
 constexpr int TC_NKB = 10;                      // ceil(300 / 32); the last block carries 12 live columns
 constexpr int TC_A_BYTES = TC_M * 128;          // 16 KB per (stage)
 constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_EPI_WARPS = 4, TC_SPLIT_WARPS = 8;
+constexpr int TC_EPI_WARPS = 8, TC_SPLIT_WARPS = 8;        // both: two warps per TMEM lane quarter
 constexpr int TC_PRODUCER_WARP = TC_EPI_WARPS + TC_SPLIT_WARPS, TC_MMA_WARP = TC_PRODUCER_WARP + 1;
 constexpr int TC_THREADS = 32 * (TC_MMA_WARP + 1);
 
@@ -136,6 +136,16 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Optional per-role timeline of CTA 0 (build with -DAIS_TC_TRACE, read with ais_debug_tc_trace): slot layout
+// trace[role][index][0..3]; roles: 0 epilogue (per tile: acc_full seen, loads done, stores done), 1 MMA (per k-block:
+// a_full seen, issued), 2 split warp 4 (per iteration: full_raw seen, computed, a_empty seen, arrived), 3 producer.
+#ifdef AIS_TC_TRACE
+__device__ long long g_tc_trace[4][256][4];
+#define TC_TRACE(role, idx, slot) do { if (blockIdx.x == 0 && (idx) < 256) g_tc_trace[role][idx][slot] = clock64(); } while (0)
+#else
+#define TC_TRACE(role, idx, slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ float rn_tf32(float x) {          // round to nearest TF32 (11 significant bits), two integer ops
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
@@ -161,7 +171,7 @@ __global__ void split_queries_kernel(const float* __restrict__ q, int nq, int n_
 // What did NOT matter (each tried): ring depth 4/6/9, 2 vs 4 vs 5 A stages, rotating vs K-range accumulators, one vs
 // two accumulator buffers at equal instruction count.  What did: the MMA issue sequence (unrolled, uniform registers:
 // 3.8 -> 2.2 ms) and the instruction count of the split and epilogue warps, which share four issue slots.
-template <int TC_N, int TC_MAIN, int TC_CROSS, int TC_RAW_STAGES, int TC_A_STAGES, int TC_NBUF>
+template <int TC_N, int TC_MAIN, int TC_CROSS, int TC_RAW_STAGES, int TC_A_STAGES, int TC_A_SUB, int TC_NBUF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_q, int64_t n,
                float* __restrict__ out, int64_t ld, uint32_t* __restrict__ max_keys, int nq_live) {
@@ -169,7 +179,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
     constexpr int TC_ACC_COLS = TC_NACC * TC_N;
     static_assert(TC_CROSS == 1 || TC_CROSS == 2 || TC_CROSS == 4, "cross accumulators");
     constexpr int TC_A_COL0 = TC_NBUF * TC_ACC_COLS;   // TMEM columns: [acc buffer(s) | A stages]
-    static_assert(TC_A_COL0 + TC_A_STAGES * 2 * TC_KB <= TC_TMEM_COLS, "TMEM budget");
+    // an A stage holds 1 / TC_A_SUB of a k-block: [hi | lo] x TC_SUB_K columns; the hand-over of a stage (commit ->
+    // split warp -> tcgen05.st -> MMA warp) takes ~900 clocks whatever its size, so what counts is how many are in flight
+    constexpr int TC_SUB_K = TC_KB / TC_A_SUB;                         // k columns per A stage
+    constexpr int TC_SUB_STEPS = TC_SUB_K / 8;                         // MMA k-steps per A stage
+    constexpr int TC_SUBS_PER_TILE = (TC_NKB - 1) * TC_A_SUB + (TC_A_SUB == 1 ? 1 : TC_A_SUB / 2);   // the last k-block has 2 live k-steps
+    static_assert(TC_A_SUB == 1 || TC_A_SUB == 2, "A sub-stages per k-block");
+    static_assert(TC_A_COL0 + TC_A_STAGES * 2 * TC_SUB_K <= TC_TMEM_COLS, "TMEM budget");
     static_assert(TC_A_STAGES <= 8 && (TC_NBUF == 1 || TC_NBUF == 2), "barrier slots");
     constexpr int TC_B_BYTES = TC_N * 128;          // one k-block of the hi (or lo) query image
     constexpr uint32_t TC_IDESC = tc_idesc(TC_N);
@@ -215,7 +231,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     const int64_t n_tiles = (n + TC_M - 1) / TC_M;
-    const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    // every CTA owns a CONTIGUOUS run of tiles: its 32 / 64 output streams sim[q][...] then advance sequentially
+    // (512 B per tile and query), which the DRAM write path likes better than 148 CTAs hopping through each stream
+    const int64_t tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * tiles_per_cta;
+    const int my_tiles = tile0 < n_tiles ? (int)(n_tiles - tile0 < tiles_per_cta ? n_tiles - tile0 : tiles_per_cta) : 0;
     const int total_it = my_tiles * TC_NKB;
 
     if (warp == TC_PRODUCER_WARP) {
@@ -230,10 +250,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
             }
             int it = 0;
             for (int t = 0; t < my_tiles; ++t) {
-                const int row0 = (int)(((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TC_M);
+                const int row0 = (int)((tile0 + t) * TC_M);
                 for (int kb = 0; kb < TC_NKB; ++kb, ++it) {
                     const int s = it % TC_RAW_STAGES;
                     mbar_wait_guarded(empty_raw + 8 * s, ((it / TC_RAW_STAGES) & 1) ^ 1, 0);
+                    TC_TRACE(3, it, 0);
                     mbar_arrive_expect_tx(full_raw + 8 * s, TC_A_BYTES);
                     tma_2d(base + TC_OFF_RAW + s * TC_A_BYTES, &tm_rows, kb * TC_KB, row0, full_raw + 8 * s);
                 }
@@ -256,34 +277,40 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
             const uint32_t acc = tmem_base + buf * TC_ACC_COLS;
 #pragma unroll
             for (int kb = 0; kb < TC_NKB; ++kb, ++it) {
-                const int as = it % TC_A_STAGES;
-                mbar_wait_guarded(a_full + 8 * as, (it / TC_A_STAGES) & 1, 3);
-                tc_fence_after();
-                const int nks = kb == TC_NKB - 1 ? 2 : 4;                  // 300 = 9*32 + 12 -> two k-steps of 8 in the last block
-                const uint32_t a_hi = tmem_base + TC_A_COL0 + as * 2 * TC_KB, a_lo = a_hi + TC_KB;
                 const uint64_t b_hi = b_hi0 + (uint64_t)(kb * (TC_B_BYTES >> 4)), b_lo = b_lo0 + (uint64_t)(kb * (TC_B_BYTES >> 4));
-                if (elect_one()) {
+                const int nsub = kb == TC_NKB - 1 ? (TC_A_SUB + 1) / 2 : TC_A_SUB;   // 300 = 9*32 + 12 -> two k-steps of 8 in the last block
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        if (ks < nks) {
-                            // Accumulators rotate with the k-step: an MMA that accumulates into the tile the previous
-                            // MMA wrote waits out the tensor pipe's latency (~100 clocks at N = 32, six times its own
-                            // duration), so consecutive MMAs target different TMEM tiles.
-                            const int g = kb * 4 + ks;                                  // k-step of the tile, 0..37
-                            const int cm = g % TC_MAIN;
-                            const int ca = TC_MAIN + (TC_CROSS == 4 ? (g & 1) * 2 : 0);
-                            const int cb = TC_CROSS == 1 ? ca : ca + 1;
-                            const bool first_c = g < (TC_CROSS == 4 ? 2 : 1);
-                            // + 2: 32 B along K inside the swizzle span, in 16-B units
-                            tc_mma_ts(acc + cm * TC_N, a_hi + ks * 8, b_hi + 2 * ks, TC_IDESC, g < TC_MAIN ? 0u : 1u);
-                            tc_mma_ts(acc + ca * TC_N, a_hi + ks * 8, b_lo + 2 * ks, TC_IDESC, first_c ? 0u : 1u);
-                            tc_mma_ts(acc + cb * TC_N, a_lo + ks * 8, b_hi + 2 * ks, TC_IDESC, (first_c && TC_CROSS != 1) ? 0u : 1u);
+                for (int h = 0; h < TC_A_SUB; ++h) {
+                    if (h >= nsub) break;
+                    const int hs = t * TC_SUBS_PER_TILE + kb * TC_A_SUB + h;
+                    const int as = hs % TC_A_STAGES;
+                    mbar_wait_guarded(a_full + 8 * as, (hs / TC_A_STAGES) & 1, 3);
+                    if (lane == 0) TC_TRACE(1, hs, 0);
+                    tc_fence_after();
+                    const uint32_t a_hi = tmem_base + TC_A_COL0 + as * 2 * TC_SUB_K, a_lo = a_hi + TC_SUB_K;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k2 = 0; k2 < TC_SUB_STEPS; ++k2) {
+                            const int ks = h * TC_SUB_STEPS + k2;                       // k-step inside the k-block
+                            if (kb < TC_NKB - 1 || ks < 2) {
+                                // Accumulators rotate with the k-step (consecutive MMAs target different TMEM tiles)
+                                const int g = kb * 4 + ks;                              // k-step of the tile, 0..37
+                                const int cm = g % TC_MAIN;
+                                const int ca = TC_MAIN + (TC_CROSS == 4 ? (g & 1) * 2 : 0);
+                                const int cb = TC_CROSS == 1 ? ca : ca + 1;
+                                const bool first_c = g < (TC_CROSS == 4 ? 2 : 1);
+                                // + 2: 32 B along K inside the swizzle span, in 16-B units
+                                tc_mma_ts(acc + cm * TC_N, a_hi + k2 * 8, b_hi + 2 * ks, TC_IDESC, g < TC_MAIN ? 0u : 1u);
+                                tc_mma_ts(acc + ca * TC_N, a_hi + k2 * 8, b_lo + 2 * ks, TC_IDESC, first_c ? 0u : 1u);
+                                tc_mma_ts(acc + cb * TC_N, a_lo + k2 * 8, b_hi + 2 * ks, TC_IDESC, (first_c && TC_CROSS != 1) ? 0u : 1u);
+                            }
                         }
+                        tc_commit(a_empty + 8 * as);
+                        if (kb == TC_NKB - 1 && h == nsub - 1) tc_commit(acc_full + 8 * buf);
+                        TC_TRACE(1, hs, 1);
                     }
-                    tc_commit(a_empty + 8 * as);
-                    if (kb == TC_NKB - 1) tc_commit(acc_full + 8 * buf);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else if (warp >= TC_EPI_WARPS) {
@@ -293,8 +320,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
         const int r = quarter * 32 + lane;                                   // row of the box = TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + TC_A_COL0;
         for (int it = g; it < total_it; it += 2) {
-            const int s = it % TC_RAW_STAGES, as = it % TC_A_STAGES;
+            const int s = it % TC_RAW_STAGES;
+            const int t = it / TC_NKB, kb = it - t * TC_NKB;
             mbar_wait_guarded(full_raw + 8 * s, (it / TC_RAW_STAGES) & 1, 4);
+            if (warp == TC_EPI_WARPS && lane == 0) TC_TRACE(2, it / 2, 0);
             const unsigned char* rowp = gbase + TC_OFF_RAW + s * TC_A_BYTES + r * 128;
             float4 x[8];
 #pragma unroll
@@ -314,53 +343,78 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
                 }
             }
             __syncwarp();
+            if (warp == TC_EPI_WARPS && lane == 0) TC_TRACE(2, it / 2, 1);
             if (lane == 0) mbar_arrive(empty_raw + 8 * s);                   // the box is in registers: refill the stage
-            mbar_wait_guarded(a_empty + 8 * as, ((it / TC_A_STAGES) & 1) ^ 1, 5);
-            tc_fence_after();
-            const uint32_t ta = lane_addr + as * 2 * TC_KB;
-            tc_st16(ta, reinterpret_cast<const uint32_t(&)[16]>(hi[0]));
-            tc_st16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(hi[16]));
-            tc_st16(ta + 32, reinterpret_cast<const uint32_t(&)[16]>(lo[0]));
-            tc_st16(ta + 48, reinterpret_cast<const uint32_t(&)[16]>(lo[16]));
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + 8 * as);
+            const int nsub = kb == TC_NKB - 1 ? (TC_A_SUB + 1) / 2 : TC_A_SUB;
+#pragma unroll
+            for (int h = 0; h < TC_A_SUB; ++h) {
+                if (h >= nsub) break;
+                const int hs = t * TC_SUBS_PER_TILE + kb * TC_A_SUB + h;
+                const int as = hs % TC_A_STAGES;
+                mbar_wait_guarded(a_empty + 8 * as, ((hs / TC_A_STAGES) & 1) ^ 1, 5);
+                if (warp == TC_EPI_WARPS && lane == 0 && h == 0) TC_TRACE(2, it / 2, 2);
+                tc_fence_after();
+                const uint32_t ta = lane_addr + as * 2 * TC_SUB_K;
+                if constexpr (TC_A_SUB == 1) {
+                    tc_st16(ta, reinterpret_cast<const uint32_t(&)[16]>(hi[0]));
+                    tc_st16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(hi[16]));
+                    tc_st16(ta + 32, reinterpret_cast<const uint32_t(&)[16]>(lo[0]));
+                    tc_st16(ta + 48, reinterpret_cast<const uint32_t(&)[16]>(lo[16]));
+                } else {
+                    tc_st16(ta, reinterpret_cast<const uint32_t(&)[16]>(hi[16 * h]));
+                    tc_st16(ta + 16, reinterpret_cast<const uint32_t(&)[16]>(lo[16 * h]));
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + 8 * as);
+                if (warp == TC_EPI_WARPS && lane == 0 && h == nsub - 1) TC_TRACE(2, it / 2, 3);
+            }
         }
     } else {
         // ---------------- epilogue warps: TMEM -> registers -> sim[q][doc] ----------------
-        // Lane = doc.  Per (doc, query): the fp32 sum of the accumulators, one coalesced store (a warp writes 128
-        // contiguous bytes of sim[q]) and one FMNMX into the lane's running maximum of that query; the lanes'
-        // maxima meet once, at the end.  Column chunks beyond the live queries of the pass are skipped (never loaded,
-        // never stored); inside the last live chunk the zero-vector padding columns are stored too - the work arrays
-        // hold a multiple of 16 rows.
-        float lmax[TC_N];
+        // Lane = doc; warp w reads TMEM lanes 32 * (w % 4) .. and the query columns of half w / 4.  A tcgen05.ld round
+        // trip costs ~700 clocks while the MMAs keep TMEM busy (measured with the CTA timeline, scratch/tc_trace.py:
+        // 8 dependent rounds per tile made the epilogue, 6000 clocks, the longest stage of the pipeline), so a warp
+        // issues all the loads of 16 query columns at once - one or two rounds per tile.  Per (doc, query): the fp32
+        // sum of the accumulators, one coalesced store (a warp writes 128 contiguous bytes of sim[q]) and one FMNMX
+        // into the lane's running maximum of that query; the lanes' maxima meet once, at the end.  Column chunks
+        // beyond the live queries of the pass are skipped; inside the last live chunk the zero-vector padding columns
+        // are stored too - the work arrays hold a multiple of 16 rows.
+        constexpr int QW = TC_N / 2;                                         // query columns per epilogue warp
+        constexpr int CH = 16;
+        const int quarter = warp & 3, half = warp >> 2;
+        float lmax[QW];
 #pragma unroll
-        for (int q = 0; q < TC_N; ++q) lmax[q] = -INFINITY;
-        constexpr int CH = TC_N > 32 ? 8 : 16;                               // columns per TMEM load: register budget
-        const int n_chunks = (nq_live + CH - 1) / CH;                        // >= 1
+        for (int q = 0; q < QW; ++q) lmax[q] = -INFINITY;
+        int n_chunks = (nq_live - half * QW + CH - 1) / CH;                  // live chunks of this warp's columns
+        n_chunks = n_chunks < 0 ? 0 : (n_chunks > QW / CH ? QW / CH : n_chunks);
         for (int t = 0; t < my_tiles; ++t) {
             const int buf = t % TC_NBUF;
             mbar_wait_guarded(acc_full + 8 * buf, (t / TC_NBUF) & 1, 6);
+            if (warp == 0 && lane == 0) TC_TRACE(0, t, 0);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * TC_ACC_COLS;
-            const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TC_M + warp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC_ACC_COLS + half * QW;
+            const int64_t row = (tile0 + t) * TC_M + quarter * 32 + lane;
             const bool live = row < n;
-            float* orow = out + row;
+            float* orow = out + row + (int64_t)(half * QW) * ld;
+            if (n_chunks == 0) {                                             // nothing to read: hand the buffer back at once
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+            }
 #pragma unroll
-            for (int c = 0; c < TC_N / CH; ++c) {
+            for (int c = 0; c < QW / CH; ++c) {
                 if (c >= n_chunks) break;                                    // warp-uniform
                 uint32_t a[TC_NACC][CH];
 #pragma unroll
-                for (int m = 0; m < TC_NACC; ++m) {
-                    if constexpr (CH == 16) tc_ld16(taddr + m * TC_N + c * CH, a[m]);
-                    else tc_ld8(taddr + m * TC_N + c * CH, a[m]);
-                }
+                for (int m = 0; m < TC_NACC; ++m) tc_ld16(taddr + m * TC_N + c * CH, a[m]);
                 tc_wait_ld();
                 if (c == n_chunks - 1) {                                     // the tile is out of TMEM: hand the buffer back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+                    if (warp == 0 && lane == 0) TC_TRACE(0, t, 1);
                 }
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
@@ -378,11 +432,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
                     }
                 }
             }
+            if (warp == 0 && lane == 0) TC_TRACE(0, t, 2);
         }
 #pragma unroll
-        for (int q = 0; q < TC_N; ++q) {
+        for (int q = 0; q < QW; ++q) {
             const float m = warp_max(lmax[q]);
-            if (lane == 0 && q < nq_live) atomicMax(&max_keys[q], fkey(m));
+            if (lane == 0 && half * QW + q < nq_live) atomicMax(&max_keys[half * QW + q], fkey(m));
         }
     }
 
