@@ -42,9 +42,14 @@ __global__ void kd_kernel(const int64_t* __restrict__ doc_len, int64_t n, double
 // independent, so their latency is hidden by parallelism instead of being paid serially in the scoring kernel.
 __global__ void bm25_slices_kernel(const int64_t* __restrict__ post_ptr, const int32_t* __restrict__ post_doc, int32_t n_vocab,
                                    const QueryTerms* __restrict__ queries, int t_cap, int64_t n_sub,
-                                   int64_t* __restrict__ slices) {
+                                   int64_t* __restrict__ slices, double magic, int32_t* __restrict__ n_required) {
     const int64_t sub = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int qi = blockIdx.y / t_cap, j = blockIdx.y - qi * t_cap;
+    if (sub == 0 && j == 0) {                            // per-query constant of the combine phase (webui.py:161)
+        int r = 0;
+        for (int t = 0; t < queries[qi].n_terms; ++t) r += queries[qi].weight[t] > magic;
+        n_required[qi] = r;
+    }
     if (sub > n_sub || j >= queries[qi].n_terms) return;
     const int t = queries[qi].term[j];
     int64_t a = 0, b = 0;
@@ -65,21 +70,12 @@ struct Bm25Args {
     // phase 0: per-query maximum + the sub-tile's record (+ optional dense scores for the compute_bm25_scores seam)
     uint64_t* max_keys; double* dense_out; int64_t ld;
     uint32_t* tile_hdr;                                        // [q][tile_ld][8]: bitmap of the docs whose BM25 value is not the default
+    const int32_t* n_required;                                 // [q] number of required terms (bm25_slices_kernel)
     // phase 1: normalise + combine with the dot scores (webui.py:376-383), store the combined scores, segment maxima
     const float* sim; double* fin; const double* maxes; double wb; float wd;
     uint64_t* seg_max; int seg_mod;                            // seg_max[q][sub % seg_mod]
     uint64_t* tile_max; int64_t tile_ld;                       // tile_max[q][sub]: best key of the sub-tile (the collect pass skips by it)
 };
-
-// number of required terms of a query (weight > magic; webui.py:161 - 1000 itself is NOT required)
-__device__ __forceinline__ int count_required(const QueryTerms& Q, double magic, int lane) {
-    int n_required = 0;
-    for (int j0 = 0; j0 < Q.n_terms; j0 += 32) {
-        const int j = j0 + lane;
-        n_required += __popc(__ballot_sync(0xffffffffu, j < Q.n_terms && Q.weight[j] > magic));
-    }
-    return n_required;
-}
 
 // Phase 0.  One WARP per (sub-tile of BM25_SUB docs, query), no block barriers: every warp runs its own dependency chain
 // (slice bounds -> postings -> K_d -> fp64 contribution -> ordered accumulation -> record), so an SM overlaps ~40 of
@@ -249,6 +245,19 @@ bm25_score_kernel(Bm25Args A) {
         atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)best);
 }
 
+// x / m rounded to nearest with three instructions (Markstein: y = RN(1/m), q = RN(x*y), r = x - m*q exactly by FMA,
+// q' = RN(q + r*y) is the correctly rounded quotient when nothing over- or underflows); operands outside a safe
+// exponent window take the full IEEE division.  webui.py:377-378 divides fp32 by fp32.
+__device__ __forceinline__ float div_by_max(float x, float m, float y, bool m_safe) {
+    const uint32_t ex = (__float_as_uint(x) >> 23) & 0xffu;
+    if (m_safe && ex - 64u < 128u) {                   // 2^-63 <= |x| < 2^65
+        const float q = __fmul_rn(x, y);
+        const float r = __fmaf_rn(-m, q, x);
+        return __fmaf_rn(r, y, q);
+    }
+    return __fdiv_rn(x, m);
+}
+
 constexpr int BM25C_WARPS = 8;
 constexpr int BM25C_THREADS = 32 * BM25C_WARPS;
 
@@ -256,7 +265,7 @@ constexpr int BM25C_THREADS = 32 * BM25C_WARPS;
 // (32-byte bitmap + compacted values), bm25 / max for the recorded docs (full warps on the fp64 division), then per
 // doc  final = wb * bm25n + wd * (sim / max sim)  (webui.py:376-383; fp32 / fp32, the products and the sum in the
 // reference's precisions), store it, and keep the sub-tile's best key for the select.
-__global__ void __launch_bounds__(BM25C_THREADS)
+__global__ void __launch_bounds__(BM25C_THREADS, 4)
 bm25_combine_kernel(Bm25Args A) {
     __shared__ double vals_all[BM25C_WARPS][BM25_SUB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -266,38 +275,51 @@ bm25_combine_kernel(Bm25Args A) {
     const int qi = blockIdx.y;
     const int64_t lo = sub * BM25_SUB;
     const int64_t hi = (lo + BM25_SUB < A.n) ? lo + BM25_SUB : A.n;
-    const double maxb = A.maxes[2 * qi];
-    const float maxs = (float)A.maxes[2 * qi + 1];
     const float* simq = A.sim + (int64_t)qi * A.ld;
     double* finq = A.fin + (int64_t)qi * A.ld;
 
-    // every lane holds the whole bitmap (two broadcast 16-byte loads)
-    const uint4* hp = reinterpret_cast<const uint4*>(A.tile_hdr + ((int64_t)qi * A.tile_ld + sub) * 8);
-    const uint4 h0 = hp[0], h1 = hp[1];
-    const uint32_t w[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    int n_rec = 0;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) n_rec += __popc(w[u]);
-
-    const int n_required = count_required(A.queries[qi], A.magic, lane);
-    double dflt = n_required > 0 ? -INFINITY : 0.0;               // bm25n of a doc without a record: 0 / max = 0, -inf / max = -inf
-    if (n_rec > 0) {
-        for (int i = lane; i < n_rec; i += 32) {
-            double v = finq[lo + i];
-            if (maxb > 0.0) v = __ddiv_rn(v, maxb);                                // webui.py:379-380
-            vals[i] = v;
-        }
-        __syncwarp();
-    }
-    const double wb_dflt = __dmul_rn(A.wb, dflt);
-
-    // the dot scores of the sub-tile first (independent loads), then the arithmetic
+    // all the independent global loads first: the dot scores of the sub-tile, the bitmap (every lane holds all of it:
+    // two broadcast 16-byte loads), the per-query constants
     float sv[BM25_SUB / 32];
 #pragma unroll
     for (int u = 0; u < BM25_SUB / 32; ++u) {
         const int64_t d = lo + u * 32 + lane;
         sv[u] = d < hi ? __ldcs(simq + d) : 0.0f;
     }
+    const uint4* hp = reinterpret_cast<const uint4*>(A.tile_hdr + ((int64_t)qi * A.tile_ld + sub) * 8);
+    const uint4 h0 = hp[0], h1 = hp[1];
+    // the first 64 record slots are fetched before the bitmap says how many there are (average: ~50): one dependent
+    // round trip less for most sub-tiles
+    double pre[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) pre[r] = lo + 32 * r + lane < hi ? finq[lo + 32 * r + lane] : 0.0;
+    const double maxb = A.maxes[2 * qi];
+    const float maxs = (float)A.maxes[2 * qi + 1];
+    const int n_required = A.n_required[qi];
+    const uint32_t mex = (__float_as_uint(maxs) >> 23) & 0xffu;
+    const bool m_safe = maxs > 0.0f && mex - 64u < 128u;          // 2^-63 <= max < 2^65
+    const float rmax = m_safe ? __frcp_rn(maxs) : 0.0f;
+    const uint32_t w[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    int n_rec = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) n_rec += __popc(w[u]);
+
+    double dflt = n_required > 0 ? -INFINITY : 0.0;               // bm25n of a doc without a record: 0 / max = 0, -inf / max = -inf
+    if (n_rec > 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = 32 * r + lane;
+            if (i < n_rec) vals[i] = maxb > 0.0 ? __ddiv_rn(pre[r], maxb) : pre[r];     // webui.py:379-380
+        }
+        for (int i = 64 + lane; i < n_rec; i += 32) {
+            double v = finq[lo + i];
+            if (maxb > 0.0) v = __ddiv_rn(v, maxb);
+            vals[i] = v;
+        }
+        __syncwarp();
+    }
+    const double wb_dflt = __dmul_rn(A.wb, dflt);
+
     double fbest = -INFINITY;
     bool any = false, nan_seen = false;
     int prefix = 0;
@@ -310,7 +332,7 @@ bm25_combine_kernel(Bm25Args A) {
         prefix += __popc(w[u]);
         if (d < hi) {
             float sn = sv[u];
-            if (maxs > 0.0f) sn = __fdiv_rn(sn, maxs);                             // webui.py:377-378 (fp32 / fp32)
+            if (maxs > 0.0f) sn = div_by_max(sn, maxs, rmax, m_safe);              // webui.py:377-378 (fp32 / fp32)
             const double f = __dadd_rn(wbb, (double)__fmul_rn(A.wd, sn));          // webui.py:383
             __stcs(finq + d, f);
             nan_seen = nan_seen || (f != f);

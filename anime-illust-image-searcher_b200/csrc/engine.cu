@@ -149,6 +149,7 @@ struct ais_engine {
     Buf fs_keys, fs_ids, fs_count;
     Buf bm25_slices;
     int bm25_t_cap = 1;
+    Buf q_nreq;                // [qt_cap] number of required terms per query
     Buf tile_hdr;              // [qt_cap][tile_ld][8] bitmap of the docs with a BM25 record (bm25.cuh)
     Buf tile_max;  int64_t tile_ld = 0;       // [qt_cap][tile_ld] best key per 256-doc tile (select2.cuh)
     Buf seg_max, sel_thr, surv_count, surv_keys, surv_ids, gate, witness, last_keys, wit_table;
@@ -247,6 +248,7 @@ int ensure_work(ais_engine* e) {
     const int64_t tl = (l + SEL_TILE - 1) / SEL_TILE;
     TRY(dev_alloc(e, e->tile_max, (size_t)q * tl * sizeof(uint64_t)));
     TRY(dev_alloc(e, e->tile_hdr, (size_t)q * tl * 8 * sizeof(uint32_t)));
+    TRY(dev_alloc(e, e->q_nreq, (size_t)q * sizeof(int32_t)));
     e->tile_ld = tl;
     TRY(dev_alloc(e, e->sel_thr, (size_t)q * sizeof(uint64_t)));
     TRY(dev_alloc(e, e->surv_count, (size_t)q * sizeof(int)));
@@ -520,6 +522,7 @@ Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
     a.fin = e->fin.as<double>();
     a.tile_hdr = e->tile_hdr.as<uint32_t>();
     a.tile_ld = e->tile_ld;
+    a.n_required = e->q_nreq.as<int32_t>();
     return a;
 }
 
@@ -533,7 +536,7 @@ int launch_bm25_max(ais_engine* e, int nq, double* dense_out) {
     TRY(dev_alloc(e, e->bm25_slices, (size_t)e->qt_cap * t_cap * (n_sub + 1) * sizeof(int64_t)));
     bm25_slices_kernel<<<dim3((unsigned)((n_sub + 1 + 127) / 128), (unsigned)(nq * t_cap)), 128, 0, e->stream>>>(
         e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->n_vocab, e->d_qt.as<QueryTerms>(), t_cap, n_sub,
-        e->bm25_slices.as<int64_t>());
+        e->bm25_slices.as<int64_t>(), e->p.require_magic, e->q_nreq.as<int32_t>());
     LAUNCHED(e);
     Bm25Args a = bm25_args(e, n_sub);
     a.max_keys = e->maxb_key.as<uint64_t>();
@@ -1095,7 +1098,7 @@ int ais_destroy(ais_engine* e) {
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
-                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->tile_max, &e->tile_hdr, &e->sel_thr, &e->surv_count,
+                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->tile_max, &e->tile_hdr, &e->q_nreq, &e->sel_thr, &e->surv_count,
                    &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices, &e->qsplit})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,

@@ -37,6 +37,7 @@ struct ScoreFinal {        // stored combined scores
         key = dkey(fin[i]);
         return true;
     }
+    __device__ __forceinline__ double val(int64_t i) const { return fin[i]; }
     __device__ __forceinline__ bool is_seed(int64_t) const { return false; }
 };
 struct ScoreRerank {       // pass 2: webui.py:208 blend; the PRF seeds are not candidates (webui.py:217)
@@ -45,6 +46,9 @@ struct ScoreRerank {       // pass 2: webui.py:208 blend; the PRF seeds are not 
         const double r = __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)__fmul_rn(cp.wr, rer[i]));
         key = dkey(r);
         return true;                 // seeds are filtered by is_seed() only for docs that would otherwise qualify
+    }
+    __device__ __forceinline__ double val(int64_t i) const {
+        return __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)__fmul_rn(cp.wr, rer[i]));
     }
     __device__ __forceinline__ bool is_seed(int64_t id) const {
         bool hit = false;
@@ -93,6 +97,11 @@ __device__ __forceinline__ uint64_t warp_max_u64_redux(uint64_t v) {
 }
 
 // ---- 1. segment maxima (+ tile maxima) ---------------------------------------------------------------
+// The stream runs in the double domain (one fmax per doc; an order-preserving key costs a dozen integer instructions
+// and made this kernel issue-bound at 71 % with DRAM at 51 %): keys are formed once per tile / segment.  A NaN score
+// (only possible with a zero weight times -inf, or NaN rows) sorts first like dkey(NaN) does: it is tracked by a flag.
+constexpr uint64_t KEY_NAN = 0xFFF8000000000000ull;
+
 template <int MODE>
 __global__ void __launch_bounds__(32 * SEG_WARPS)
 segmax_kernel(SelectArgs a) {
@@ -104,47 +113,60 @@ segmax_kernel(SelectArgs a) {
         __syncthreads();
     }
     const int seg = blockIdx.x * SEG_WARPS + warp;
-    uint64_t best = KEY_EMPTY, all_best = KEY_EMPTY;
+    uint64_t all_best = KEY_EMPTY;
     if (seg < a.n_seg) {
         const int64_t tiles_per_seg = a.seg_len / SEL_TILE;
         const int64_t t0 = (int64_t)seg * tiles_per_seg;
         const int64_t t1 = t0 + tiles_per_seg < a.n_tiles ? t0 + tiles_per_seg : a.n_tiles;
         uint64_t* tmax = a.tile_max + (int64_t)qi * a.tile_ld;
+        double bestd = -INFINITY;              // best non-seed score of the segment so far (valid once `has`)
+        bool has = false, best_nan = false;
         with_functor<MODE>(a, qi, seeds, [&](auto& f) {
 #pragma unroll 1
             for (int64_t tile = t0; tile < t1; ++tile) {
                 const int64_t lo = tile * SEL_TILE;
                 const int64_t hi = lo + SEL_TILE < a.n ? lo + SEL_TILE : a.n;
-                uint64_t tbest = KEY_EMPTY;
-                int64_t i = lo + lane;
-#pragma unroll 1
-                for (; i + 96 < hi; i += 128) {
-                    uint64_t k0, k1, k2, k3;
-                    f(i, a.id_base + i, k0);
-                    f(i + 32, a.id_base + i + 32, k1);
-                    f(i + 64, a.id_base + i + 64, k2);
-                    f(i + 96, a.id_base + i + 96, k3);
-                    const uint64_t m01 = k0 > k1 ? k0 : k1, m23 = k2 > k3 ? k2 : k3;
-                    const uint64_t m = m01 > m23 ? m01 : m23;
-                    tbest = m > tbest ? m : tbest;
-                    if (m > best) {                       // rare after the first few iterations
-                        if (k0 > best && !f.is_seed(a.id_base + i)) best = k0;
-                        if (k1 > best && !f.is_seed(a.id_base + i + 32)) best = k1;
-                        if (k2 > best && !f.is_seed(a.id_base + i + 64)) best = k2;
-                        if (k3 > best && !f.is_seed(a.id_base + i + 96)) best = k3;
+                double tb = -INFINITY;
+                bool tnan = false, tany = false;
+                // the PRF seeds are not candidates (webui.py:217); at most `depth` of the shard's tiles hold one, so
+                // the per-doc seed test runs only there (a lane-private "new best?" test is NOT rare: a lane meets
+                // only 160 docs per segment, and some lane of the warp finds a new best in nearly every tile)
+                const bool seeded = MODE == 2 && __any_sync(0xffffffffu, lane < a.depth && seeds[lane] >= a.id_base + lo &&
+                                                                             seeds[lane] < a.id_base + hi);
+                if (hi - lo == SEL_TILE && !seeded) {
+                    // all 8 docs of a lane are loaded before any arithmetic (16 loads in flight per lane)
+                    double rr[SEL_TILE / 32];
+#pragma unroll
+                    for (int u = 0; u < SEL_TILE / 32; ++u) rr[u] = f.val(lo + 32 * u + lane);
+                    double m = rr[0];
+                    bool nn = rr[0] != rr[0];
+#pragma unroll
+                    for (int u = 1; u < SEL_TILE / 32; ++u) { m = fmax(m, rr[u]); nn = nn || (rr[u] != rr[u]); }
+                    tb = m;
+                    tnan = nn;
+                    tany = true;
+                    bestd = fmax(bestd, m);
+                    best_nan = best_nan || nn;
+                    has = true;
+                } else {
+                    for (int64_t i = lo + lane; i < hi; i += 32) {
+                        const double r = f.val(i);
+                        tnan = tnan || (r != r);
+                        tb = fmax(tb, r);
+                        tany = true;
+                        if ((r > bestd || !has || r != r) && !f.is_seed(a.id_base + i)) {
+                            if (r != r) best_nan = true; else if (r > bestd || !has) bestd = r;
+                            has = true;
+                        }
                     }
                 }
-                for (; i < hi; i += 32) {
-                    uint64_t k;
-                    f(i, a.id_base + i, k);
-                    tbest = k > tbest ? k : tbest;
-                    if (k > best && !f.is_seed(a.id_base + i)) best = k;
-                }
+                uint64_t tbest = tnan ? KEY_NAN : (tany ? dkey(tb) : KEY_EMPTY);
                 tbest = warp_max_u64_redux(tbest);
                 if (lane == 0) tmax[tile] = tbest;
                 all_best = tbest > all_best ? tbest : all_best;
             }
         });
+        uint64_t best = best_nan ? KEY_NAN : (has ? dkey(bestd) : KEY_EMPTY);
         best = warp_max_u64(best);
         if (lane == 0) a.seg_max[(size_t)qi * SEG_MAX + seg] = best;
     }

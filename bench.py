@@ -33,6 +33,29 @@ VOCAB = 10861
 SEED = 20260101
 
 
+def scan_kernel_for(batch: int):
+    """(kernel name, key into profiles/traffic.json) of the scan launch that dominates a batch of this size"""
+    left = min(batch, 128)
+    if left >= 33:
+        return "scan_tc_kernel<64> (tcgen05 kind::tf32 3xTF32, 64 queries per pass)", "scan_tc64"
+    if left >= 9:
+        return "scan_tc_kernel<32> (tcgen05 kind::tf32 3xTF32, 32 queries per pass)", "scan_tc32"
+    if left >= 5:
+        return "scan_mma_kernel<8> (mma.sync 3xTF32)", "scan_mma8"
+    return "scan_kernel<%d> (fp32 SIMT, lane per row)" % (1 if left <= 1 else 2 if left <= 2 else 4), "scan_simt"
+
+
+def load_traffic(key: str, n_docs_local: int):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum at 10 M docs), scaled to this shard's rows; None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)[key]
+        return float(t["dram_bytes_per_launch"]) * n_docs_local / float(t["docs"]), t["source"]
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -161,7 +184,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--docs", type=int, default=10_000_000)
-    ap.add_argument("--batch", type=int, default=64, help="queries per engine batch (1..128); every 16 share one pass over the doc vectors")
+    ap.add_argument("--batch", type=int, default=64, help="queries per engine batch (1..128); up to 64 share one pass over the doc vectors")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-docs", type=int, default=100_000)
     ap.add_argument("--cpu-queries", type=int, default=12)
@@ -281,6 +304,9 @@ def main():
     step_bytes = 2 * scan_bytes + post_bytes / args.steps
     step_gbs = step_bytes / (dev_ms / args.steps * 1e-3) / 1e9
 
+    kernel_name, traffic_key = scan_kernel_for(b)
+    traffic, traffic_src = load_traffic(traffic_key, hi - lo)
+
     sweep = None
     if args.sweep or not args.no_modes:
         # other operating points of the same engine: batch 1 = single-query latency mode (both scans at the HBM
@@ -315,14 +341,16 @@ def main():
             "dtype": "f32 dot / f64 BM25+combine", "data": "synthetic",
             "config": {"workload": "%d docs sharded over %d GPU(s), V=%d, ~30 distinct tags/doc (%d postings on rank 0), 300-d fp32 rows; "
                                    "weighted queries with +required/-exclude, top-%d, PRF re-rank (device stored-rows mode); "
-                                   "%d queries per pass" % (args.docs, world, VOCAB, nnz_local, TOPN, b),
+                                   "%d queries per engine batch" % (args.docs, world, VOCAB, nnz_local, TOPN, b),
                        "docs": args.docs, "batch": b, "topn": TOPN, "prf": "stored_rows", "parallelism": "doc-shard x%d" % world,
                        "l2": "inputs larger than L2 (%.1f GB of rows per GPU re-read every pass)" % (scan_bytes / 1e9)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "how": "host wall clock around the public API call (ctypes -> C ABI) with host query buffers and host result arrays"},
             "gpu_launches": int(st["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "scan_kernel (doc-vector scan, %d launches)" % st["scan_launches"],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "%s, %d launches" % (kernel_name, st["scan_launches"]),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
+                         "traffic_frac": (traffic / (scan_ms * 1e-3) / 1e9 / peak) if traffic and scan_ms > 0 else None,
                          "peak_source": peak_src, "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms,
                          "scan_share_of_step": st["scan_ms_total"] / dev_ms,
                          "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak}},

@@ -94,6 +94,36 @@ def test_fresh_index_vs_oracle(n_docs, vocab, tf_frac):
                                                lambda: P.find_sorted(q), 1e-6, topn, q)
 
 
+def test_config1_10k_docs_1024_queries_batched():
+    """BASELINE.json configs[0] / SURVEY.md 8(d) config 1: 10^4 docs, V = 10 861, 1 024 weighted queries with +required /
+    -exclude tags, top-100, PRF on - every result of the batched engine path (64 queries per pass: tcgen05 scan, BM25
+    records, tile-filtered select) against the oracle's find_similar_documents: ids, order, scores, exceptions."""
+    from ais_b200.engine import raise_for_status
+    idx = synth.generate_index(10000, vocab_size=10861, seed=20260101)
+    P = port.OraclePort(idx)
+    texts = synth.generate_queries(idx, 1024, seed=1)
+    t2i = idx.token2id
+    infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
+    qs = [Q.make_query(t, t2i, infer) for t in texts]
+    eng = E.SearchEngine.from_index(idx, max_batch=64)
+    n_err = 0
+    for b0 in range(0, len(qs), 64):
+        ids, scores, counts, status, _ = eng.search_raw(qs[b0:b0 + 64], 100, E.PRF_STORED_ROWS)
+        for j in range(len(ids)):
+            text = texts[b0 + j]
+            want = capture(P.find_similar_documents, text, 100)
+            try:
+                raise_for_status(int(status[j]))
+                c = int(counts[j])
+                got = ("ok", ids[j, :c].tolist(), scores[j, :c].tolist())
+            except Exception as e:   # noqa: BLE001
+                got = ("err", type(e).__name__, str(e))
+                n_err += 1
+            assert_same_or_filter_unstable(got, want, lambda: P.find_sorted(text), 1e-6, 100, text)
+    eng.close()
+    assert n_err < 1024            # the generator rejects most queries that leave fewer than 10 docs
+
+
 def test_batched_queries_equal_single_queries():
     """<= 4 queries per pass run the same fp32 SIMT scan (bit-equal results for any batching); >= 5 queries per
     pass run a tensor-core scan (3xTF32, fp32-level accuracy; mma.sync up to 16, tcgen05 beyond): same ranking within
