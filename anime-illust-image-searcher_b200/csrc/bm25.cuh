@@ -88,7 +88,7 @@ struct Bm25Args {
 // required term) in tile_hdr, and those values, compacted in doc order, in the first slots of the sub-tile's own range
 // of the combined-score array `fin` (which phase 1 of the same warp position overwrites with the final scores).  Phase 1
 // therefore never touches posting lists, K_d or an fp64 division per posting again.
-__global__ void __launch_bounds__(BM25_THREADS)
+__global__ void __launch_bounds__(BM25_THREADS, 5)
 bm25_score_kernel(Bm25Args A) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -218,7 +218,8 @@ bm25_score_kernel(Bm25Args A) {
     // ---- record: bitmap + compacted values (doc order), and the maximum over the sub-tile ----
     // webui.py:160,168: excluded hit, or a required term missing -> -inf (absorbing under +=)
     double* rec = A.fin + (int64_t)qi * A.ld + lo;
-    uint64_t best = KEY_EMPTY;
+    double bd = -INFINITY;                                        // maximum in the double domain, one key at the end
+    bool any = false;
     int n_rec = 0;
 #pragma unroll
     for (int u = 0; u < BM25_SUB / 32; ++u) {
@@ -231,15 +232,16 @@ bm25_score_kernel(Bm25Args A) {
         if (lane == 0) hdr[u] = m;
         if (rec_it) {
             rec[n_rec + __popc(m & ((1u << lane) - 1u))] = v;
-            const uint64_t k = dkey(v);
-            best = k > best ? k : best;
+            bd = fmax(bd, v);
+            any = true;
         }
         n_rec += __popc(m);
     }
     if (n_rec < (int)(hi - lo)) {                                 // some doc keeps the default
-        const uint64_t k = dkey(untouched);
-        best = k > best ? k : best;
+        bd = fmax(bd, untouched);
+        any = true;
     }
+    uint64_t best = any ? dkey(bd) : KEY_EMPTY;
     best = warp_max_u64(best);
     if (lane == 0 && best > *(volatile uint64_t*)&A.max_keys[qi])
         atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)best);
