@@ -164,6 +164,8 @@ struct ais_engine {
     int h_out_cap = 0;
 
     // stats
+    int64_t column_scan_launches = 0;
+    bool requery_dense = false;    // AIS_REQUERY_DENSE=1: always run the dense scan for the PRF re-query
     int64_t scan_launches = 0, kernel_launches = 0, fullsort_fallbacks = 0, bytes_device = 0;
     bool profiling = false;
     bool use_mma = true;       // >= 5 queries per pass: tensor-core scan (3xTF32); AIS_SCAN_SIMT=1 keeps the fp32 SIMT kernel
@@ -448,6 +450,20 @@ int launch_scan_one(ais_engine* e, const float* d_q, int nq, float* out, uint32_
     return launch_scan_t<16>(e, d_q, nq, out, max_keys);
 }
 
+// queries with a single non-zero component `comp` (the reference's PRF re-query): one sector per doc
+int launch_scan_column(ais_engine* e, const float* d_q, int nq, int comp, float* out, uint32_t* max_keys) {
+    if (e->n_vec == 0) return AIS_OK;
+    int64_t gx = (e->n_vec + COL_THREADS - 1) / COL_THREADS;
+    if (gx > 8LL * e->sm_count) gx = 8LL * e->sm_count;
+    cudaEvent_t a = nullptr, b = nullptr;
+    column_scan_kernel<<<dim3((unsigned)gx, (unsigned)((nq + COL_QC - 1) / COL_QC)), COL_THREADS, 0, e->stream>>>(
+        e->rows.as<float>(), e->n_vec, comp, d_q, nq, out, e->ld, max_keys);
+    LAUNCHED(e);
+    (void)a; (void)b;
+    e->column_scan_launches++;
+    return AIS_OK;
+}
+
 // one pass over the rows per MAX_QT queries (the query buffer is zero-padded to a power of two >= nq)
 int launch_scan(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
     if (e->n_vec == 0) return AIS_OK;
@@ -728,7 +744,18 @@ int do_requery_select(ais_engine* e, int nq, int k, uint64_t* d_keys, int64_t* d
 int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows, int prf_mode, int k, double* d_max_r,
                uint64_t* d_keys, int64_t* d_ids) {
     const int depth = e->p.prf_depth;
+    // Does every re-query vector have at most one non-zero component, the same one for the whole batch?  The collapsed
+    // centroid of the reference always does (component 0); a caller-supplied vector is inspected.
+    int comp = -1;
     if (q2_host) {
+        comp = -2;                                               // -2: no non-zero seen yet
+        for (int q = 0; q < nq && comp != -1; ++q)
+            for (int j = 0; j < DIM; ++j)
+                if (q2_host[(size_t)q * DIM + j] != 0.0f) {
+                    if (comp == -2) comp = j;
+                    else if (comp != j) { comp = -1; break; }
+                }
+        if (comp == -2) comp = 0;
         const int padded = next_pow2_int(nq);
         memcpy(e->h_q2, q2_host, (size_t)nq * DIM * sizeof(float));
         for (int i = nq; i < padded; ++i) memset(e->h_q2 + (size_t)i * DIM, 0, DIM * sizeof(float));
@@ -744,11 +771,14 @@ int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows,
                                                    prf_mode == AIS_PRF_STORED_ROWS ? 1 : 0, e->d_q2.as<float>(),
                                                    e->status.as<int32_t>());
         LAUNCHED(e);
+        if (prf_mode == AIS_PRF_STORED_ROWS) comp = 0;          // [c, 0, ..., 0] by construction (or all zero)
     }
+    if (e->requery_dense) comp = -1;
     init_keys_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
                                              e->maxr_key.as<uint64_t>(), e->status.as<int32_t>(), nq, 2);
     LAUNCHED(e);
-    TRY(launch_scan(e, e->d_q2.as<float>(), nq, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
+    if (comp >= 0) TRY(launch_scan_column(e, e->d_q2.as<float>(), nq, comp, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
+    else TRY(launch_scan(e, e->d_q2.as<float>(), nq, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
     TRY(do_requery_select(e, nq, k, d_keys, d_ids));
     maxr_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxr_key.as<uint64_t>(), nq, d_max_r);
     LAUNCHED(e);
@@ -1084,6 +1114,7 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
     e->use_mma = !(simt && simt[0] == '1');
     if (const char* tcm = getenv("AIS_SCAN_TC_MIN")) e->tc_min = atoi(tcm);
     if (const char* tcw = getenv("AIS_SCAN_TC_WIDE")) e->tc_wide = atoi(tcw) != 0;
+    if (const char* rd = getenv("AIS_REQUERY_DENSE")) e->requery_dense = atoi(rd) != 0;
     int s = set_scan_attrs();
     if (s != AIS_OK) { cudaStreamDestroy(e->own_stream); delete e; return s; }
     *out = e;
@@ -1573,13 +1604,14 @@ int ais_get_stats(ais_engine* e, ais_stats* out) {
     out->kernel_launches = e->kernel_launches;
     out->fullsort_fallbacks = e->fullsort_fallbacks;
     out->bytes_device = e->bytes_device;
+    out->column_scan_launches = e->column_scan_launches;
     return AIS_OK;
 }
 int ais_reset_stats(ais_engine* e) {
     if (!e) return fail(AIS_ERR_INVALID, "NULL engine");
     DeviceGuard g(e->device);
     TRY(drain_events(e));
-    e->scan_launches = e->kernel_launches = e->fullsort_fallbacks = 0;
+    e->scan_launches = e->kernel_launches = e->fullsort_fallbacks = e->column_scan_launches = 0;
     e->scan_ms_total = 0.0;
     return AIS_OK;
 }

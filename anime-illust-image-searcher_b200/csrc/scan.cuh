@@ -309,4 +309,46 @@ scan_mma_kernel(const float* __restrict__ rows, int64_t n, const float* __restri
         }
 }
 
+// =================================================================================================
+// column_scan_kernel: the scan for query vectors with ONE non-zero component.
+//
+// The reference's PRF re-query (webui.py:200-205) is such a vector: the (300,2) array of (index, value) pairs is
+// normalised as a whole and its indices are round()-ed to 0, gensim's sparse2full keeps the last value for id 0, so
+// index[.] receives [c, 0, ..., 0] and its scores are rows[d][0] * c - numpy's fp32 dot product of a
+// row with that vector is exactly RN(rows[d][0] * c), every other product being +-0.  Reading one 32-byte sector per
+// doc instead of the 1200-byte row gives the same bits for 1/37 of the traffic, shared by all queries of the batch.
+// =================================================================================================
+constexpr int COL_QC = 16;            // queries per block row
+constexpr int COL_THREADS = 256;
+
+__global__ void __launch_bounds__(COL_THREADS)
+column_scan_kernel(const float* __restrict__ rows, int64_t n, int comp, const float* __restrict__ queries,  // [nq][DIM]
+                   int nq, float* __restrict__ out, int64_t ld, uint32_t* __restrict__ max_keys) {
+    __shared__ float c[COL_QC];
+    const int q0 = blockIdx.y * COL_QC;
+    const int live = nq - q0 < COL_QC ? nq - q0 : COL_QC;
+    if (threadIdx.x < COL_QC) c[threadIdx.x] = threadIdx.x < live ? queries[(size_t)(q0 + threadIdx.x) * DIM + comp] : 0.0f;
+    __syncthreads();
+    float lmax[COL_QC];
+#pragma unroll
+    for (int q = 0; q < COL_QC; ++q) lmax[q] = -INFINITY;
+    const int64_t stride = (int64_t)gridDim.x * COL_THREADS;
+    for (int64_t d = (int64_t)blockIdx.x * COL_THREADS + threadIdx.x; d < n; d += stride) {
+        const float x = __ldg(rows + d * DIM + comp);
+#pragma unroll
+        for (int q = 0; q < COL_QC; ++q) {
+            if (q < live) {
+                const float v = __fmul_rn(x, c[q]);
+                out[(int64_t)(q0 + q) * ld + d] = v;
+                lmax[q] = fmaxf(lmax[q], v);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < COL_QC; ++q) {
+        const float m = warp_max(lmax[q]);
+        if ((threadIdx.x & 31) == 0 && q < live && m > -INFINITY) atomicMax(&max_keys[q0 + q], fkey(m));
+    }
+}
+
 }  // namespace ais

@@ -191,6 +191,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the extra batch-1 / batch-4 operating points")
     ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1,2,4,8,16 (extra key batch_sweep)")
+    ap.add_argument("--prf", default="stored_rows", choices=["stored_rows", "full"],
+                    help="stored_rows: the reference's re-query (collapsed centroid [c,0,...,0]: served by the one-sector-per-doc "
+                         "column scan); full: the un-collapsed centroid (a second dense pass over the rows)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -236,7 +239,7 @@ def main():
     pool = [E.Query(*p) for p in parsed]
     eng.use_torch_stream()                               # CUDA events below see the engine's kernels
     S = shard.ShardedSearch([eng], args.docs) if world > 1 else None
-    mode = E.PRF_STORED_ROWS
+    mode = E.PRF_STORED_ROWS if args.prf == "stored_rows" else E.PRF_STORED_ROWS_FULL
 
     def search(qs):
         # one GPU: the C-ABI call ais_search; several: the staged calls with NCCL between them
@@ -301,7 +304,9 @@ def main():
     for s in range(args.steps):
         for q in batch_at(args.warmup + s, b):
             post_bytes += int(sum(4 * df_host[t] for t in q.term_ids)) // world
-    step_bytes = 2 * scan_bytes + post_bytes / args.steps
+    # pass 2: the reference's collapsed re-query needs column 0 only (4 B per doc); the dense variant a second full pass
+    requery_bytes = (hi - lo) * 4 if st["column_scan_launches"] > 0 else scan_bytes
+    step_bytes = scan_bytes + requery_bytes + post_bytes / args.steps
     step_gbs = step_bytes / (dev_ms / args.steps * 1e-3) / 1e9
 
     kernel_name, traffic_key = scan_kernel_for(b)
@@ -324,7 +329,8 @@ def main():
             sweep[str(bb)] = {"qps": k * bb / (ms * 1e-3), "e2e_qps": k * bb / (wms * 1e-3), "scan_ms": sm,
                               "scan_gbs": scan_bytes / (sm * 1e-3) / 1e9, "scan_frac_of_peak": scan_bytes / (sm * 1e-3) / 1e9 / peak,
                               "scan_share": s2["scan_ms_total"] / ms,
-                              "whole_step_frac_of_peak": (2 * scan_bytes * bb) / (ms / k * 1e-3) / 1e9 / peak / bb}
+                              "whole_step_frac_of_peak": ((scan_bytes + ((hi - lo) * 4 if s2["column_scan_launches"] > 0 else scan_bytes)) * bb)
+                                                         / (ms / k * 1e-3) / 1e9 / peak / bb}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -342,7 +348,8 @@ def main():
             "config": {"workload": "%d docs sharded over %d GPU(s), V=%d, ~30 distinct tags/doc (%d postings on rank 0), 300-d fp32 rows; "
                                    "weighted queries with +required/-exclude, top-%d, PRF re-rank (device stored-rows mode); "
                                    "%d queries per engine batch" % (args.docs, world, VOCAB, nnz_local, TOPN, b),
-                       "docs": args.docs, "batch": b, "topn": TOPN, "prf": "stored_rows", "parallelism": "doc-shard x%d" % world,
+                       "docs": args.docs, "batch": b, "topn": TOPN, "prf": args.prf,
+                       "requery": "column scan (single non-zero component, SURVEY.md A.5)" if st["column_scan_launches"] > 0 else "dense scan", "parallelism": "doc-shard x%d" % world,
                        "l2": "inputs larger than L2 (%.1f GB of rows per GPU re-read every pass)" % (scan_bytes / 1e9)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "how": "host wall clock around the public API call (ctypes -> C ABI) with host query buffers and host result arrays"},

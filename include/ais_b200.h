@@ -102,6 +102,7 @@ typedef struct ais_stats {
     int64_t kernel_launches;    /* all kernels launched by the engine since the last reset */
     int64_t fullsort_fallbacks; /* times the ambiguous-filter fallback sorted the whole shard */
     int64_t bytes_device;       /* device memory held by the engine */
+    int64_t column_scan_launches; /* re-query passes served by the single-component column scan */
 } ais_stats;
 
 const char* ais_last_error(void);

@@ -182,6 +182,32 @@ def test_tensor_core_scan_accuracy(mb):
     eng.close()
 
 
+def test_requery_column_scan_equals_dense_scan(monkeypatch):
+    """The reference's PRF re-query vector is [c, 0, ..., 0]; the engine serves it with a column scan
+    (one sector per doc).  Same bits as the dense fp32 scan of that vector, same search results, and it is counted."""
+    idx = synth.generate_index(30000, vocab_size=1500, seed=91)
+    queries = synth.generate_queries(idx, 8, seed=5)
+    t2i = idx.token2id
+    infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
+    qs = [Q.make_query(q, t2i, infer) for q in queries]
+    out = {}
+    for dense in ("1", "0"):
+        monkeypatch.setenv("AIS_REQUERY_DENSE", dense)
+        eng = E.SearchEngine.from_index(idx, max_batch=1)
+        eng.reset_stats()
+        res, rers = [], []
+        for q in qs:
+            res.append(eng.search_raw([q], 100, E.PRF_STORED_ROWS))
+            rers.append(eng.debug_read("rer", 0))
+        out[dense] = (res, rers, eng.stats()["column_scan_launches"])
+        eng.close()
+    assert out["1"][2] == 0 and out["0"][2] == len(qs)
+    for (a, ra), (b, rb) in zip(zip(out["1"][0], out["1"][1]), zip(out["0"][0], out["0"][1])):
+        assert np.array_equal(ra, rb)                                  # fp32 SIMT dense scan == column scan, bit for bit
+        for x, y in zip(a[:4], b[:4]):
+            assert np.array_equal(x, y)
+
+
 def test_constants_are_honoured_at_call_time():
     idx = synth.generate_index(6000, vocab_size=500, seed=5)
     P = port.OraclePort(idx)
