@@ -165,6 +165,9 @@ struct ais_engine {
 
     // stats
     int64_t column_scan_launches = 0;
+    Buf colbuf;                    // rows[.][col_comp] as a compact array (column mode of the PRF re-query)
+    int col_comp = -1;  const void* col_rows_ptr = nullptr;  int64_t col_n = -1;
+    bool rer_column = false;       // current batch: rer[q][d] = colbuf[d] * d_q2[q][col_comp], never materialised
     bool requery_dense = false;    // AIS_REQUERY_DENSE=1: always run the dense scan for the PRF re-query
     int64_t scan_launches = 0, kernel_launches = 0, fullsort_fallbacks = 0, bytes_device = 0;
     bool profiling = false;
@@ -450,17 +453,34 @@ int launch_scan_one(ais_engine* e, const float* d_q, int nq, float* out, uint32_
     return launch_scan_t<16>(e, d_q, nq, out, max_keys);
 }
 
+struct RerRef { const float* base; int64_t qstride; const float* scale; };
+RerRef rer_ref(const ais_engine* e) {
+    if (e->rer_column) return {e->colbuf.as<float>(), 0, e->d_q2.as<float>() + e->col_comp};
+    return {e->rer.as<float>(), e->ld, nullptr};
+}
+
+// column mode of the re-query: make sure colbuf holds column `comp` of the current rows (extracted once per index)
+int prepare_column(ais_engine* e, int comp) {
+    TRY(dev_alloc(e, e->colbuf, (size_t)(e->n_vec > 0 ? e->n_vec : 1) * sizeof(float)));
+    if (e->col_comp != comp || e->col_rows_ptr != e->rows.p || e->col_n != e->n_vec) {
+        if (e->n_vec > 0) {
+            extract_column_kernel<<<(unsigned)((e->n_vec + 255) / 256), 256, 0, e->stream>>>(e->rows.as<float>(), e->n_vec, comp,
+                                                                                        e->colbuf.as<float>());
+            LAUNCHED(e);
+        }
+        e->col_comp = comp; e->col_rows_ptr = e->rows.p; e->col_n = e->n_vec;
+    }
+    return AIS_OK;
+}
+
 // queries with a single non-zero component `comp` (the reference's PRF re-query): one sector per doc
 int launch_scan_column(ais_engine* e, const float* d_q, int nq, int comp, float* out, uint32_t* max_keys) {
     if (e->n_vec == 0) return AIS_OK;
     int64_t gx = (e->n_vec + COL_THREADS - 1) / COL_THREADS;
     if (gx > 8LL * e->sm_count) gx = 8LL * e->sm_count;
-    cudaEvent_t a = nullptr, b = nullptr;
     column_scan_kernel<<<dim3((unsigned)gx, (unsigned)((nq + COL_QC - 1) / COL_QC)), COL_THREADS, 0, e->stream>>>(
         e->rows.as<float>(), e->n_vec, comp, d_q, nq, out, e->ld, max_keys);
     LAUNCHED(e);
-    (void)a; (void)b;
-    e->column_scan_launches++;
     return AIS_OK;
 }
 
@@ -619,7 +639,8 @@ int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, 
     TRY(ensure_sel(e, k));
     const int64_t n = e->n();
     SelectArgs a;
-    a.sim = e->sim.as<float>(); a.fin = e->fin.as<double>(); a.rer = e->rer.as<float>();
+    const RerRef rr = rer_ref(e);
+    a.sim = e->sim.as<float>(); a.fin = e->fin.as<double>(); a.rer = rr.base; a.rer_qstride = rr.qstride; a.rer_scale = rr.scale;
     a.n = n; a.ld = e->ld; a.id_base = e->first_doc;
     a.cp = combine_params(e);
     a.maxes = d_maxes;
@@ -670,7 +691,7 @@ int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, 
                                                                        e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
     else
         rerank_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
-            e->fin.as<double>(), e->rer.as<float>(), n, e->ld, a.cp, e->first_doc, e->top_ids.as<int64_t>(), e->p.prf_depth, k,
+            e->fin.as<double>(), rr.base, rr.qstride, rr.scale, n, e->ld, a.cp, e->first_doc, e->top_ids.as<int64_t>(), e->p.prf_depth, k,
             e->maxr_key.as<uint64_t>(), e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
     LAUNCHED(e);
     return merge_lists(e, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), G, k, (int64_t)G * k, k, k, nq, d_keys, d_ids,
@@ -692,6 +713,7 @@ int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
     LAUNCHED(e);
     e->cur_nq = nq;
     e->cur_prf = false;
+    e->rer_column = false;
     return AIS_OK;
 }
 
@@ -777,7 +799,8 @@ int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows,
     init_keys_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(),
                                              e->maxr_key.as<uint64_t>(), e->status.as<int32_t>(), nq, 2);
     LAUNCHED(e);
-    if (comp >= 0) TRY(launch_scan_column(e, e->d_q2.as<float>(), nq, comp, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
+    e->rer_column = comp >= 0;
+    if (comp >= 0) { TRY(prepare_column(e, comp)); e->column_scan_launches++; }      // no per-query array: col[d] * c_q on the fly
     else TRY(launch_scan(e, e->d_q2.as<float>(), nq, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
     TRY(do_requery_select(e, nq, k, d_keys, d_ids));
     maxr_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxr_key.as<uint64_t>(), nq, d_max_r);
@@ -851,7 +874,9 @@ int do_witness(ais_engine* e, int nq, const int32_t* amb, const uint64_t* last_k
         CK(cudaMemsetAsync(e->wit_table.p, 0, (size_t)WITNESS_BUCKETS * sizeof(uint64_t), e->stream));
         WitnessArgs a;
         a.fin = e->fin.as<double>() + (size_t)q * e->ld;
-        a.rer = e->rer.as<float>() + (size_t)q * e->ld;
+        const RerRef rr = rer_ref(e);
+        a.rer = rr.base + (size_t)q * rr.qstride;
+        a.rer_scale = rr.scale ? rr.scale + (size_t)q * DIM : nullptr;
         a.n = e->n();
         a.id_base = e->first_doc;
         a.cp = combine_params(e);
@@ -899,8 +924,10 @@ int bitonic_sort(ais_engine* e, uint64_t* keys, int64_t* ids, int64_t n_pad) {
 // write this shard's keys of query qi (pass 2: R, seeds blanked; pass 1: finals) into caller arrays [n_local]
 int do_export_keys(ais_engine* e, int qi, int second_pass, uint64_t* d_keys, int64_t* d_ids) {
     if (e->n() == 0) return AIS_OK;
+    const RerRef rr = rer_ref(e);
     fill_keys_kernel<<<(unsigned)((e->n() + 255) / 256), 256, 0, e->stream>>>(
-        e->fin.as<double>() + (size_t)qi * e->ld, e->rer.as<float>() + (size_t)qi * e->ld, e->n(), combine_params(e),
+        e->fin.as<double>() + (size_t)qi * e->ld, rr.base + (size_t)qi * rr.qstride, rr.scale ? rr.scale + (size_t)qi * DIM : nullptr,
+        e->n(), combine_params(e),
         second_pass ? 1 : 0, e->first_doc, e->top_ids.as<int64_t>() + (size_t)qi * MAX_DEPTH, second_pass ? e->p.prf_depth : 0,
         d_keys, d_ids, e->n());
     LAUNCHED(e);
@@ -1129,7 +1156,7 @@ int ais_destroy(ais_engine* e) {
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
-                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->tile_max, &e->tile_hdr, &e->q_nreq, &e->sel_thr, &e->surv_count,
+                   &e->out_count, &e->out_amb, &e->fs_keys, &e->fs_ids, &e->fs_count, &e->seg_max, &e->tile_max, &e->tile_hdr, &e->q_nreq, &e->colbuf, &e->sel_thr, &e->surv_count,
                    &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices, &e->qsplit})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,
@@ -1554,6 +1581,9 @@ int ais_debug_read(ais_engine* e, int32_t which, int32_t query, void* out) {
     if (!e || !out || query < 0 || query >= e->qt_cap || which < 0 || which > 3) return fail(AIS_ERR_INVALID, "bad argument");
     DeviceGuard g(e->device);
     const size_t n = (size_t)e->n();
+    if (which == 3 && e->rer_column && e->n_vec > 0)        // column mode keeps no rer array: materialise this query's row
+        TRY(launch_scan_column(e, e->d_q2.as<float>() + (size_t)query * DIM, 1, e->col_comp, e->rer.as<float>() + (size_t)query * e->ld,
+                               e->maxs_key.as<uint32_t>() + query));
     const void* src = which == 0 ? (const void*)(e->sim.as<float>() + (size_t)query * e->ld)
                     : which == 1 ? (const void*)(e->bm25.as<double>())
                     : which == 2 ? (const void*)(e->fin.as<double>() + (size_t)query * e->ld)

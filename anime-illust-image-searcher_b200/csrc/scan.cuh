@@ -351,4 +351,11 @@ column_scan_kernel(const float* __restrict__ rows, int64_t n, int comp, const fl
     }
 }
 
+// column `comp` of the row matrix as a compact fp32 array (40 MB at 10 M docs: L2-resident for all queries of a batch).
+// The pass-2 kernels form rer[d] = RN(col[d] * c_q) on the fly, so the collapsed re-query needs no per-query array at all.
+__global__ void extract_column_kernel(const float* __restrict__ rows, int64_t n, int comp, float* __restrict__ col) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) col[d] = __ldg(rows + d * DIM + comp);
+}
+
 }  // namespace ais

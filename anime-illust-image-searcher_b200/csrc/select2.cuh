@@ -41,14 +41,14 @@ struct ScoreFinal {        // stored combined scores
     __device__ __forceinline__ bool is_seed(int64_t) const { return false; }
 };
 struct ScoreRerank {       // pass 2: webui.py:208 blend; the PRF seeds are not candidates (webui.py:217)
-    const double* fin; const float* rer; CombineParams cp; const int64_t* seeds; int depth;
+    const double* fin; const float* rer; float cq; CombineParams cp; const int64_t* seeds; int depth;   // rer[i] * cq: see RerankF
     __device__ __forceinline__ bool operator()(int64_t i, int64_t id, uint64_t& key) const {
-        const double r = __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)__fmul_rn(cp.wr, rer[i]));
+        const double r = __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)__fmul_rn(cp.wr, __fmul_rn(rer[i], cq)));
         key = dkey(r);
         return true;                 // seeds are filtered by is_seed() only for docs that would otherwise qualify
     }
     __device__ __forceinline__ double val(int64_t i) const {
-        return __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)__fmul_rn(cp.wr, rer[i]));
+        return __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)__fmul_rn(cp.wr, __fmul_rn(rer[i], cq)));
     }
     __device__ __forceinline__ bool is_seed(int64_t id) const {
         bool hit = false;
@@ -59,6 +59,8 @@ struct ScoreRerank {       // pass 2: webui.py:208 blend; the PRF seeds are not 
 
 struct SelectArgs {        // everything the three kernels share
     const float* sim; double* fin; const float* rer;
+    int64_t rer_qstride;        // ld, or 0 when `rer` is the shared column buffer
+    const float* rer_scale;     // null (scale 1) or the queries' scalars [q * DIM]
     int64_t n, ld, id_base;
     CombineParams cp;
     const double* maxes;        // [nq][2] (mode 0)
@@ -83,7 +85,8 @@ __device__ __forceinline__ void with_functor(const SelectArgs& a, int qi, const 
         ScoreFinal f{a.fin + (size_t)qi * a.ld};
         body(f);
     } else {
-        ScoreRerank f{a.fin + (size_t)qi * a.ld, a.rer + (size_t)qi * a.ld, a.cp, seeds_smem, a.depth};
+        ScoreRerank f{a.fin + (size_t)qi * a.ld, a.rer + (size_t)qi * a.rer_qstride,
+                      a.rer_scale ? a.rer_scale[(size_t)qi * DIM] : 1.0f, a.cp, seeds_smem, a.depth};
         body(f);
     }
 }
@@ -304,6 +307,7 @@ sort_survivors_kernel(const int* __restrict__ surv_count, const uint64_t* __rest
 // ---- near-tie witness ------------------------------------------------------------------------------------
 struct WitnessArgs {
     const double* fin; const float* rer;      // rows of the query
+    const float* rer_scale;                   // null (1) or the query's scalar (column mode)
     int64_t n, id_base;
     CombineParams cp;
     int second_pass;                          // 1: value = normalised blend R (seeds skipped); 0: combined score
@@ -325,13 +329,14 @@ witness_kernel(WitnessArgs a) {
     if (threadIdx.x < MAX_DEPTH) seeds[threadIdx.x] = (a.second_pass && threadIdx.x < a.depth) ? a.seeds[threadIdx.x] : -1;
     __syncthreads();
     const double max_r = a.max_r ? *a.max_r : 0.0;
+    const float cq = a.rer_scale ? *a.rer_scale : 1.0f;
     const double v_last = a.last_key == ~0ull ? 1.0 : witness_value(a.normalize, max_r, dkey_inv(a.last_key));
     const uint64_t neg_inf = dkey(-INFINITY);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         if (*((volatile int*)a.flag)) return;                   // somebody found one
         double raw = a.fin[i];
-        if (a.second_pass) raw = __dadd_rn(__dmul_rn(a.cp.wo, raw), (double)__fmul_rn(a.cp.wr, a.rer[i]));
+        if (a.second_pass) raw = __dadd_rn(__dmul_rn(a.cp.wo, raw), (double)__fmul_rn(a.cp.wr, __fmul_rn(a.rer[i], cq)));
         const uint64_t key = dkey(raw);
         if (key > a.last_key || key <= neg_inf) continue;       // inside the prefix region / masked
         const int64_t id = a.id_base + i;
