@@ -29,12 +29,16 @@ struct QueryTerms {  // device-resident, one per query of the pass
 };
 
 __global__ void kd_kernel(const int64_t* __restrict__ doc_len, int64_t n, double avgdl, double k1, double b,
-                          double one_minus_b, double* __restrict__ kd) {
+                          double one_minus_b, double k1p1, double* __restrict__ kd, double* __restrict__ g1) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     // k1 * (1 - b + b * (dl / bm25_avgdl))      webui.py:145
     const double r = __ddiv_rn((double)doc_len[i], avgdl);
-    kd[i] = __dmul_rn(k1, __dadd_rn(one_minus_b, __dmul_rn(b, r)));
+    const double k = __dmul_rn(k1, __dadd_rn(one_minus_b, __dmul_rn(b, r)));
+    kd[i] = k;
+    // tf == 1 (every real tagger output: tags of an image are unique): tf*(k1+1) / (tf + K_d) with the same operations,
+    // once per doc instead of once per posting and query            webui.py:145-147
+    g1[i] = __ddiv_rn(__dmul_rn(1.0, k1p1), __dadd_rn(1.0, k));
 }
 
 // slices[(q * t_cap + j) * (n_sub + 1) + sub] = first posting of query q's j-th term whose doc id is
@@ -65,7 +69,7 @@ __global__ void bm25_slices_kernel(const int64_t* __restrict__ post_ptr, const i
 struct Bm25Args {
     const int64_t* slices; int t_cap; int64_t n_sub;
     const int32_t* post_doc; const int32_t* post_tf;          // post_tf may be null: tf == 1
-    const double* idf; const double* kd; int64_t n; int32_t n_vocab;
+    const double* idf; const double* kd; const double* g1; int64_t n; int32_t n_vocab;   // g1: the tf == 1 quotient per doc
     const QueryTerms* queries; double magic, k1p1;
     // phase 0: per-query maximum + the sub-tile's record (+ optional dense scores for the compute_bm25_scores seam)
     uint64_t* max_keys; double* dense_out; int64_t ld;
@@ -164,10 +168,16 @@ bm25_score_kernel(Bm25Args A) {
                 const int t = Q.term[j];
                 const double mult = (w > A.magic) ? (w - A.magic) : w;
                 const double idfv = (t >= 0 && t < A.n_vocab) ? A.idf[t] : 0.0;
-                const double tf = A.post_tf ? (double)A.post_tf[p] : 1.0;
-                const double denom = __dadd_rn(tf, A.kd[d]);                       // webui.py:145
-                const double numer = __dmul_rn(tf, A.k1p1);                        // webui.py:146
-                const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));     // webui.py:147
+                double quot;
+                if (A.post_tf) {
+                    const double tf = (double)A.post_tf[p];
+                    const double denom = __dadd_rn(tf, A.kd[d]);                   // webui.py:145
+                    const double numer = __dmul_rn(tf, A.k1p1);                    // webui.py:146
+                    quot = __ddiv_rn(numer, denom);
+                } else {
+                    quot = A.g1[d];                                                // the same quotient for tf == 1, precomputed
+                }
+                const double score = __dmul_rn(idfv, quot);                        // webui.py:147
                 c = __dmul_rn(mult, score);                                        // webui.py:167,170
             }
             st_doc[e] = (uint8_t)(d - lo);
@@ -202,10 +212,14 @@ bm25_score_kernel(Bm25Args A) {
                 const double idfv = (t >= 0 && t < A.n_vocab) ? A.idf[t] : 0.0;
                 for (int64_t p = a + lane; p < b; p += 32) {
                     const int d = A.post_doc[p];
-                    const double tf = A.post_tf ? (double)A.post_tf[p] : 1.0;
-                    const double denom = __dadd_rn(tf, A.kd[d]);
-                    const double numer = __dmul_rn(tf, A.k1p1);
-                    const double score = __dmul_rn(idfv, __ddiv_rn(numer, denom));
+                    double quot;
+                    if (A.post_tf) {
+                        const double tf = (double)A.post_tf[p];
+                        quot = __ddiv_rn(__dmul_rn(tf, A.k1p1), __dadd_rn(tf, A.kd[d]));
+                    } else {
+                        quot = A.g1[d];
+                    }
+                    const double score = __dmul_rn(idfv, quot);
                     const int l = (int)(d - lo);
                     acc[l] = __dadd_rn(acc[l], __dmul_rn(mult, score));
                     if (required) reqc[l] = (uint8_t)(reqc[l] + 1);

@@ -133,7 +133,7 @@ struct ais_engine {
 
     // index
     Buf rows;  int64_t n_vec = 0, cap_vec = 0;
-    Buf post_ptr, post_doc, post_tf, idf, kd, doc_len;
+    Buf post_ptr, post_doc, post_tf, idf, kd, g1, doc_len;
     double avgdl = 0.0;
     bool has_tf = false;
     int32_t n_vocab = 0;
@@ -549,6 +549,7 @@ Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
     a.post_tf = e->has_tf ? e->post_tf.as<int32_t>() : nullptr;
     a.idf = e->idf.as<double>();
     a.kd = e->kd.as<double>();
+    a.g1 = e->g1.as<double>();
     a.n = e->n_bm25;
     a.n_vocab = e->n_vocab;
     a.queries = e->d_qt.as<QueryTerms>();
@@ -1152,7 +1153,7 @@ int ais_destroy(ais_engine* e) {
     if (!e) return AIS_OK;
     DeviceGuard g(e->device);
     cudaStreamSynchronize(e->stream);
-    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->doc_len, &e->sim, &e->bm25, &e->fin,
+    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->g1, &e->doc_len, &e->sim, &e->bm25, &e->fin,
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
@@ -1177,7 +1178,8 @@ int ais_set_params(ais_engine* e, const ais_params* p) {
     e->p = *p;
     if (kd_stale) {
         kd_kernel<<<(unsigned)((e->n_bm25 + 255) / 256), 256, 0, e->stream>>>(e->doc_len.as<int64_t>(), e->n_bm25, e->avgdl, e->p.k1,
-                                                                             e->p.b, 1.0 - e->p.b, e->kd.as<double>());
+                                                                             e->p.b, 1.0 - e->p.b, e->p.k1 + 1.0, e->kd.as<double>(),
+                                                                             e->g1.as<double>());
         LAUNCHED(e);
     }
     return AIS_OK;
@@ -1261,11 +1263,13 @@ int ais_load_bm25(ais_engine* e, const int64_t* post_ptr, const int32_t* post_do
     if (n_terms > 0) CK(cudaMemcpyAsync(e->idf.p, idf, (size_t)n_terms * sizeof(double), cudaMemcpyDefault, e->stream));
     TRY(dev_alloc(e, e->doc_len, (size_t)n_docs * sizeof(int64_t)));
     TRY(dev_alloc(e, e->kd, (size_t)n_docs * sizeof(double)));
+    TRY(dev_alloc(e, e->g1, (size_t)n_docs * sizeof(double)));
     if (n_docs > 0) {
         CK(cudaMemcpyAsync(e->doc_len.p, doc_len, (size_t)n_docs * sizeof(int64_t), cudaMemcpyDefault, e->stream));
         // webui.py:145  k1 * (1 - b + b * (dl / bm25_avgdl)), same operation order, no contraction
         kd_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, e->stream>>>(e->doc_len.as<int64_t>(), n_docs, avgdl, e->p.k1, e->p.b,
-                                                                          1.0 - e->p.b, e->kd.as<double>());
+                                                                          1.0 - e->p.b, e->p.k1 + 1.0, e->kd.as<double>(),
+                                                                          e->g1.as<double>());
         LAUNCHED(e);
     }
     CK(cudaStreamSynchronize(e->stream));
@@ -1352,9 +1356,11 @@ int ais_finish_bm25(ais_engine* e, const double* idf, double avgdl) {
     TRY(dev_alloc(e, e->idf, (size_t)e->n_vocab * sizeof(double)));
     CK(cudaMemcpyAsync(e->idf.p, idf, (size_t)e->n_vocab * sizeof(double), cudaMemcpyDefault, e->stream));
     TRY(dev_alloc(e, e->kd, (size_t)n_docs * sizeof(double)));
+    TRY(dev_alloc(e, e->g1, (size_t)n_docs * sizeof(double)));
     if (n_docs > 0) {
         kd_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, e->stream>>>(e->doc_len.as<int64_t>(), n_docs, avgdl, e->p.k1, e->p.b,
-                                                                          1.0 - e->p.b, e->kd.as<double>());
+                                                                          1.0 - e->p.b, e->p.k1 + 1.0, e->kd.as<double>(),
+                                                                          e->g1.as<double>());
         LAUNCHED(e);
     }
     CK(cudaStreamSynchronize(e->stream));
