@@ -190,7 +190,7 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the extra batch-1 / batch-4 operating points")
-    ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1,2,4,8,16 (extra key batch_sweep)")
+    ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1..128 (extra key batch_sweep): SIMT -> mma.sync -> tcgen05 crossover")
     ap.add_argument("--prf", default="stored_rows", choices=["stored_rows", "full"],
                     help="stored_rows: the reference's re-query (collapsed centroid [c,0,...,0]: served by the one-sector-per-doc "
                          "column scan); full: the un-collapsed centroid (a second dense pass over the rows)")
@@ -220,7 +220,7 @@ def main():
     # ---- stage the shard [lo, hi) of the synthetic index into HBM -----------------------------------
     t_build = time.perf_counter()
     lo, hi = shard.shard_bounds(args.docs, world, rank)
-    eng = E.SearchEngine(device=local_rank, max_batch=max(args.batch, 64) if args.sweep else args.batch)
+    eng = E.SearchEngine(device=local_rank, max_batch=max(args.batch, 128) if args.sweep else args.batch)
     rows = eng.rows_tensor(hi - lo)
     sh = synth_torch.generate_shard(lo, hi, rows, vocab=VOCAB, seed=SEED)
     idf, avgdl, df = synth_torch.global_stats(sh, args.docs)
@@ -317,7 +317,7 @@ def main():
         # other operating points of the same engine: batch 1 = single-query latency mode (both scans at the HBM
         # roofline), batch 4 = largest batch of the fp32 SIMT scan; --sweep adds the rest
         sweep = {}
-        for bb in ((1, 2, 4, 8, 16, 32, 64) if args.sweep else (1, 4)):
+        for bb in ((1, 2, 4, 8, 16, 32, 64, 128) if args.sweep else (1, 4)):
             if bb > eng.params.max_batch:
                 break
             run_steps(2, bb, 0)
@@ -326,7 +326,8 @@ def main():
             s2 = eng.stats(); eng.set_profiling(False)
             k = max(4, args.steps // 2)
             sm = s2["scan_ms_total"] / max(1, s2["scan_launches"])
-            sweep[str(bb)] = {"qps": k * bb / (ms * 1e-3), "e2e_qps": k * bb / (wms * 1e-3), "scan_ms": sm,
+            sweep[str(bb)] = {"qps": k * bb / (ms * 1e-3), "e2e_qps": k * bb / (wms * 1e-3), "scan_kernel": scan_kernel_for(bb)[0],
+                              "scan_ms": sm,
                               "scan_gbs": scan_bytes / (sm * 1e-3) / 1e9, "scan_frac_of_peak": scan_bytes / (sm * 1e-3) / 1e9 / peak,
                               "scan_share": s2["scan_ms_total"] / ms,
                               "whole_step_frac_of_peak": ((scan_bytes + ((hi - lo) * 4 if s2["column_scan_launches"] > 0 else scan_bytes)) * bb)
