@@ -283,7 +283,7 @@ constexpr int BM25C_THREADS = 32 * BM25C_WARPS;
 // reference's precisions), store it, and keep the sub-tile's best key for the select.
 __global__ void __launch_bounds__(BM25C_THREADS, 4)
 bm25_combine_kernel(Bm25Args A) {
-    __shared__ double vals_all[BM25C_WARPS][BM25_SUB];
+    __shared__ double vals_all[BM25C_WARPS][BM25_SUB + 1];        // + 1: the branch-free lookup below may touch slot n_rec
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t sub = (int64_t)blockIdx.x * BM25C_WARPS + warp;
     if (sub >= A.n_sub) return;
@@ -338,22 +338,52 @@ bm25_combine_kernel(Bm25Args A) {
 
     double fbest = -INFINITY;
     bool any = false, nan_seen = false;
-    int prefix = 0;
     const unsigned lt = (1u << lane) - 1u;
+    // Fast path (all but the last sub-tile of a shard, ordinary magnitudes): no branch per doc.  The exact division
+    // runs as three instructions; the record lookup is a select (the slot index is always in bounds); a NaN score is
+    // detected by a running sum (the scores are finite or -inf, so the sum is NaN only if a score is).
+    bool ok = m_safe && hi - lo == BM25_SUB;
 #pragma unroll
     for (int u = 0; u < BM25_SUB / 32; ++u) {
-        const int64_t d = lo + u * 32 + lane;
-        double wbb = wb_dflt;
-        if ((w[u] >> lane) & 1u) wbb = __dmul_rn(A.wb, vals[prefix + __popc(w[u] & lt)]);
-        prefix += __popc(w[u]);
-        if (d < hi) {
-            float sn = sv[u];
-            if (maxs > 0.0f) sn = div_by_max(sn, maxs, rmax, m_safe);              // webui.py:377-378 (fp32 / fp32)
+        const uint32_t ex = (__float_as_uint(sv[u]) >> 23) & 0xffu;
+        ok = ok && (ex - 64u < 128u || sv[u] == 0.0f);
+    }
+    if (__all_sync(0xffffffffu, ok)) {
+        double* fp = finq + lo + lane;
+        double fsum = 0.0;
+        int prefix = 0;
+#pragma unroll
+        for (int u = 0; u < BM25_SUB / 32; ++u) {
+            const float x = sv[u];
+            const float q = __fmul_rn(x, rmax);                                    // webui.py:377-378 (fp32 / fp32), see div_by_max
+            const float sn = __fmaf_rn(__fmaf_rn(-maxs, q, x), rmax, q);
+            const double v = vals[prefix + __popc(w[u] & lt)];
+            const double wbb = ((w[u] >> lane) & 1u) ? __dmul_rn(A.wb, v) : wb_dflt;
+            prefix += __popc(w[u]);
             const double f = __dadd_rn(wbb, (double)__fmul_rn(A.wd, sn));          // webui.py:383
-            __stcs(finq + d, f);
-            nan_seen = nan_seen || (f != f);
-            fbest = any ? fmax(fbest, f) : f;
-            any = true;
+            __stcs(fp + u * 32, f);
+            fsum += f;
+            fbest = fmax(fbest, f);
+        }
+        any = true;
+        nan_seen = fsum != fsum;
+    } else {
+        int prefix = 0;
+#pragma unroll
+        for (int u = 0; u < BM25_SUB / 32; ++u) {
+            const int64_t d = lo + u * 32 + lane;
+            double wbb = wb_dflt;
+            if ((w[u] >> lane) & 1u) wbb = __dmul_rn(A.wb, vals[prefix + __popc(w[u] & lt)]);
+            prefix += __popc(w[u]);
+            if (d < hi) {
+                float sn = sv[u];
+                if (maxs > 0.0f) sn = div_by_max(sn, maxs, rmax, m_safe);          // webui.py:377-378 (fp32 / fp32)
+                const double f = __dadd_rn(wbb, (double)__fmul_rn(A.wd, sn));      // webui.py:383
+                __stcs(finq + d, f);
+                nan_seen = nan_seen || (f != f);
+                fbest = any ? fmax(fbest, f) : f;
+                any = true;
+            }
         }
     }
     uint64_t best = any ? dkey(fbest) : KEY_EMPTY;
