@@ -19,7 +19,7 @@ constexpr int BM25_SUB = 256;                    // docs per warp-private sub-ti
 constexpr int BM25_WARPS = 8;                    // warps (= consecutive sub-tiles of one query) per block
 constexpr int BM25_THREADS = 32 * BM25_WARPS;
 constexpr int BM25_STAGE = 256;                  // staged postings per (sub-tile, query); denser slices take the direct path
-constexpr int BM25_WARP_SMEM = BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8 + 3 * BM25_SUB;
+constexpr int BM25_WARP_SMEM = BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8 + 2 * BM25_SUB;
 constexpr int BM25_SMEM = BM25_WARPS * BM25_WARP_SMEM;
 
 struct QueryTerms {  // device-resident, one per query of the pass
@@ -103,8 +103,7 @@ bm25_score_kernel(Bm25Args A) {
     double* st_val = reinterpret_cast<double*>(base + BM25_SUB * 8);
     int* off = reinterpret_cast<int*>(base + BM25_SUB * 8 + BM25_STAGE * 8);                 // [MAX_TERMS + 1]
     int64_t* sl_a = reinterpret_cast<int64_t*>(base + BM25_SUB * 8 + BM25_STAGE * 8 + 264);  // [MAX_TERMS]
-    uint8_t* excl = base + BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8;
-    uint8_t* reqc = excl + BM25_SUB;
+    uint8_t* reqc = base + BM25_SUB * 8 + BM25_STAGE * 8 + 264 + MAX_TERMS * 8;
     uint8_t* st_doc = reqc + BM25_SUB;
 
     const int qi = blockIdx.y;
@@ -153,7 +152,14 @@ bm25_score_kernel(Bm25Args A) {
         return;
     }
 
-    for (int i = lane; i < BM25_SUB; i += 32) { acc[i] = 0.0; excl[i] = 0; reqc[i] = 0; }
+    // An excluded doc simply becomes -inf in its accumulator (absorbing under the later additions, webui.py:160); the
+    // per-doc count of required terms exists only for queries that have one (30 % of the benchmark's queries).
+    const bool has_req = n_required > 0;
+#pragma unroll
+    for (int u = 0; u < BM25_SUB / 32; ++u) acc[u * 32 + lane] = 0.0;
+    if (has_req)
+#pragma unroll
+        for (int u = 0; u < BM25_SUB / 32; ++u) reqc[u * 32 + lane] = 0;
     __syncwarp();
     if (E <= BM25_STAGE) {
         // ---- stage every posting of the sub-tile with its contribution (all global loads independent) ----
@@ -190,7 +196,7 @@ bm25_score_kernel(Bm25Args A) {
             const bool required = w > A.magic;
             for (int e = off[j] + lane; e < off[j + 1]; e += 32) {
                 const int l = st_doc[e];
-                if (w < 0.0) excl[l] = 1;                                          // webui.py:154-160
+                if (w < 0.0) acc[l] = -INFINITY;                                   // webui.py:154-160
                 else {
                     acc[l] = __dadd_rn(acc[l], st_val[e]);
                     if (required) reqc[l] = (uint8_t)(reqc[l] + 1);
@@ -205,7 +211,7 @@ bm25_score_kernel(Bm25Args A) {
             const int t = Q.term[j];
             const int64_t a = sl_a[j], b = a + (off[j + 1] - off[j]);
             if (w < 0.0) {
-                for (int64_t p = a + lane; p < b; p += 32) excl[A.post_doc[p] - lo] = 1;
+                for (int64_t p = a + lane; p < b; p += 32) acc[A.post_doc[p] - lo] = -INFINITY;
             } else {
                 const bool required = w > A.magic;
                 const double mult = required ? (w - A.magic) : w;
@@ -239,7 +245,8 @@ bm25_score_kernel(Bm25Args A) {
     for (int u = 0; u < BM25_SUB / 32; ++u) {
         const int l = u * 32 + lane;
         const bool in = lo + l < hi;
-        const double v = (excl[l] || reqc[l] != n_required) ? -INFINITY : acc[l];
+        double v = acc[l];
+        if (has_req && reqc[l] != n_required) v = -INFINITY;      // webui.py:168: a required term is missing
         if (A.dense_out && in) A.dense_out[(int64_t)qi * A.ld + lo + l] = v;
         const bool rec_it = in && v != untouched;                 // NaN never appears: idf, K_d and the weights are finite
         const unsigned m = __ballot_sync(0xffffffffu, rec_it);
@@ -256,7 +263,12 @@ bm25_score_kernel(Bm25Args A) {
         any = true;
     }
     uint64_t best = any ? dkey(bd) : KEY_EMPTY;
-    best = warp_max_u64(best);
+    {   // 64-bit warp maximum with two redux.sync
+        const uint32_t bh = (uint32_t)(best >> 32), bl = (uint32_t)best;
+        const uint32_t mh = __reduce_max_sync(0xffffffffu, bh);
+        const uint32_t ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
+        best = ((uint64_t)mh << 32) | ml;
+    }
     if (lane == 0 && best > *(volatile uint64_t*)&A.max_keys[qi])
         atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)best);
 }
