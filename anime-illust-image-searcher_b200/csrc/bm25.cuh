@@ -4,12 +4,14 @@
 // dict order,  score = idf * (tf*(k1+1) / (tf + k1*(1 - b + b*(dl/avgdl))))  over ALL docs and then
 // scores += weight*score  /  -inf masks.  Docs without the term get tf = 0 -> score = +0, which
 // leaves the running sum unchanged, so walking only the posting list is exact.  fp64 addition is not
-// associative, so the per-doc accumulation ORDER must be the query's term order: each CTA owns a
-// tile of BM25_TILE consecutive docs (accumulators in shared memory), reads every term's slice of its
-// posting list from a table built by bm25_slices_kernel (doc ids are ascending), and processes the terms
-// one after another with a barrier in between.  All arithmetic uses the _rn intrinsics (no FMA contraction).
+// associative, so the per-doc accumulation ORDER must be the query's term order: each WARP owns a
+// sub-tile of BM25_SUB consecutive docs for one query (accumulators in shared memory), reads every term's
+// slice of its posting list from a table built by bm25_slices_kernel (doc ids are ascending), and adds the
+// terms one after another.  All arithmetic uses the _rn intrinsics (no FMA contraction).
 //
-// K_d = k1*(1 - b + b*(dl/avgdl)) is precomputed per doc at load time with the same operation order.
+// K_d = k1*(1 - b + b*(dl/avgdl)) and, for tf == 1, the whole quotient (k1+1)/(1 + K_d) are precomputed per doc
+// at load time with the same operation order.  Two kernels around the global maxima (webui.py:379 divides by the
+// maximum over ALL docs): bm25_score_kernel leaves a compact per-sub-tile record, bm25_combine_kernel reads it.
 #pragma once
 #include "common.cuh"
 

@@ -2,12 +2,13 @@
 // bm25.cuh and select.cuh.  One engine == one GPU == one contiguous shard of the documents.
 //
 // Per query batch (<= max_batch queries share every pass over the doc vectors):
-//   stage_score    bm25_kernel (fp64, bit-exact)  +  scan_kernel (fp32 dot, one pass over the rows)
-//                  -> this shard's {max bm25, max dot}                      webui.py:352,374
-//   stage_combine  final = 0.5*bm25/max + 0.5*dot/max, block top-k, merge    webui.py:376-383,191-195
+//   stage_score    bm25_score_kernel (fp64, bit-exact, per-tile records)  +  one scan kernel (fp32 / 3xTF32 dot,
+//                  one pass over the rows) -> this shard's {max bm25, max dot}                      webui.py:352,374
+//   stage_combine  bm25_combine_kernel: final = 0.5*bm25/max + 0.5*dot/max; streaming select          webui.py:376-383,191-195
 //   stage_top      global top-`depth` docs (PRF seeds), optional row gather  webui.py:193-199
-//   stage_requery  re-query vector (host callback or device centroid), 2nd scan,
-//                  R = 0.7*final + 0.3*rer, max(R), block top-k without the seeds  webui.py:200-217
+//   stage_requery  re-query vector (host callback or device centroid); its scores: column 0 times a scalar for the
+//                  reference's collapsed centroid, else a 2nd dense scan; R = 0.7*final + 0.3*rer, max(R),
+//                  streaming select without the seeds                              webui.py:200-217
 //   stage_finish   merge, normalise, filter_searched_result, [:topn]         webui.py:219-246,63-80
 // ais_search chains the stages on one GPU; a doc-sharded caller puts its collectives between them.
 #include <cuda_runtime.h>

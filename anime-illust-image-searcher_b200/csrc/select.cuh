@@ -141,54 +141,13 @@ __device__ __forceinline__ void block_max_to_global(uint64_t v, uint64_t* wscrat
     }
 }
 
-// ---- pass 1: final = BM25_WEIGHT*bm25n + DOC2VEC_WEIGHT*simn (webui.py:376-383) + local top-k ----
+// ---- weights of the combine (webui.py:376-383, done by bm25_combine_kernel) and of the PRF blend (webui.py:208) ----
 struct CombineParams {
     double wb;   // BM25_WEIGHT     (python float * float64 array -> fp64 multiply)
     float wd;    // DOC2VEC_WEIGHT  (python float * float32 array -> fp32 multiply)
     double wo;   // ORIGINAL_SCORE_WEIGHT
     float wr;    // RERANKED_SCORE_WEIGHT (fp32 multiply, same reason)
 };
-
-struct CombineF {
-    const float* sim;
-    const double* bm25;
-    double* final_out;
-    float maxs;
-    double maxb;
-    CombineParams cp;
-    int64_t id_base;
-    __device__ __forceinline__ bool operator()(int64_t i, uint64_t& key, int64_t& id) const {
-        float s = sim[i];
-        double b = bm25[i];
-        if (maxs > 0.0f) s = __fdiv_rn(s, maxs);           // webui.py:377-378 (fp32 / fp32)
-        if (maxb > 0.0) b = __ddiv_rn(b, maxb);            // webui.py:379-380
-        const float hs = __fmul_rn(cp.wd, s);
-        const double f = __dadd_rn(__dmul_rn(cp.wb, b), (double)hs);   // webui.py:383
-        final_out[i] = f;
-        key = dkey(f);
-        id = id_base + i;
-        return true;
-    }
-};
-
-// maxes: [nq][2] doubles {max bm25, max sim}.  Candidates out: [nq][gridDim.x][k].
-__global__ void __launch_bounds__(SEL_THREADS)
-combine_select_kernel(const float* __restrict__ sim, const double* __restrict__ bm25, double* __restrict__ final_out,
-                      int64_t n, int64_t ld, const double* __restrict__ maxes, CombineParams cp, int64_t id_base,
-                      int k, uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids, const int* __restrict__ gate) {
-    __shared__ SelBuf sb;
-    const int qi = blockIdx.y;
-    if (gate && !gate[qi]) return;          // only runs when the streaming select overflowed (select2.cuh)
-    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * chunk;
-    const int64_t hi = lo + chunk < n ? lo + chunk : n;
-    sel_init(sb);
-    CombineF f{sim + qi * ld, bm25 + qi * ld, final_out + qi * ld, (float)maxes[2 * qi + 1], maxes[2 * qi], cp, id_base};
-    if (lo < hi) sel_stream(sb, lo, hi, k, f);
-    else { __syncthreads(); sel_prune(sb, k); }
-    const size_t o = ((size_t)qi * gridDim.x + blockIdx.x) * (size_t)k;
-    sel_write(sb, k, cand_keys + o, cand_ids + o);
-}
 
 // select straight from stored final scores (no-PRF branch webui.py:247-253 and ais_rerank)
 struct FinalF {
