@@ -1217,6 +1217,7 @@ int ais_reserve_docs(ais_engine* e, int64_t n_docs) {
 }
 
 int ais_load_vectors(ais_engine* e, const float* rows, int64_t n, int32_t dim, int64_t first_row) {
+    if (e) e->col_comp = -1;                 // cached column of the row store (PRF re-query) is stale now
     if (!e || (!rows && n > 0) || n < 0 || first_row < 0) return fail(AIS_ERR_INVALID, "bad argument");
     if (dim != DIM) return fail(AIS_ERR_UNSUPPORTED, "vector dimension %d: only %d (genmodel.py:16 VECTOR_LENGTH) is built", dim, DIM);
     if (first_row > e->n_vec) return fail(AIS_ERR_INVALID, "first_row %lld leaves a gap after %lld loaded rows", (long long)first_row, (long long)e->n_vec);
@@ -1234,6 +1235,7 @@ int ais_load_vectors(ais_engine* e, const float* rows, int64_t n, int32_t dim, i
 }
 
 int ais_vectors_device_ptr(ais_engine* e, int64_t n_docs, float** out_rows) {
+    if (e) e->col_comp = -1;                 // the caller is about to (re)write rows in place
     if (!e || !out_rows || n_docs < 0) return fail(AIS_ERR_INVALID, "bad argument");
     TRY(ais_reserve_docs(e, n_docs));
     e->n_vec = n_docs;

@@ -127,7 +127,9 @@ int ais_load_vectors(ais_engine* e, const float* rows, int64_t n, int32_t dim, i
 /* Pre-size the row store (avoids re-allocation while gensim shards are appended one by one). */
 int ais_reserve_docs(ais_engine* e, int64_t n_docs);
 /* Declare n_docs rows resident and hand out the device pointer of the row store [n_docs x 300] so a
- * caller that already has the rows on the device (or generates them there) can write them in place. */
+ * caller that already has the rows on the device (or generates them there) can write them in place.
+ * The rows must be final before the next search: the engine caches derived data (column 0 for the
+ * collapsed PRF re-query); call this again (or ais_load_vectors) after changing rows. */
 int ais_vectors_device_ptr(ais_engine* e, int64_t n_docs, float** out_rows);
 /* The BM25 index of genmodel.py:51-99 (bm25_corpus / bm25_idf / bm25_doc_lengths / bm25_avgdl) as
  * tag-major posting lists with LOCAL doc ids ascending inside each list.  post_tf may be NULL

@@ -270,6 +270,28 @@ def test_requery_column_scan_equals_dense_scan(monkeypatch):
             assert np.array_equal(x, y)
 
 
+def test_column_cache_follows_row_updates():
+    """The engine caches column 0 of the row store for the collapsed PRF re-query; reloading rows must refresh it."""
+    idx = synth.generate_index(8000, vocab_size=600, seed=3)
+    t2i = idx.token2id
+    infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
+    q = Q.make_query(synth.generate_queries(idx, 1, seed=8)[0], t2i, infer)
+    eng = E.SearchEngine.from_index(idx, max_batch=1)
+    eng.search_raw([q], 50, E.PRF_STORED_ROWS)
+    r1 = eng.debug_read("rer", 0)
+    rows2 = idx.rows.copy()
+    rows2[:, 0] = -3.0 * rows2[:, 0] + 0.25
+    eng.load_vectors(rows2)
+    eng.search_raw([q], 50, E.PRF_STORED_ROWS)
+    r2 = eng.debug_read("rer", 0)
+    assert not np.array_equal(r1, r2)
+    # r2 = RN(rows2[:, 0] * c) for the new re-query scalar c: recover c from one doc and check all the others
+    d0 = int(np.argmax(np.abs(rows2[:, 0])))
+    c = np.float32(r2[d0] / rows2[d0, 0])
+    assert np.allclose(r2, rows2[:, 0] * c, rtol=2e-6, atol=0)
+    eng.close()
+
+
 def test_constants_are_honoured_at_call_time():
     idx = synth.generate_index(6000, vocab_size=500, seed=5)
     P = port.OraclePort(idx)
