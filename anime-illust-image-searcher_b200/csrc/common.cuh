@@ -14,7 +14,7 @@ constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;  // 38400 B per TMA bulk copy
 
 constexpr int MAX_TERMS = 64;                    // AIS_MAX_TERMS
 constexpr int MAX_QT = 16;                       // queries sharing one pass over the doc vectors (one scan launch)
-constexpr int MAX_BATCH = 128;                   // queries per engine batch (ceil(nq / MAX_QT) scan launches per pass)
+constexpr int MAX_BATCH = 256;                   // queries per engine batch (BASELINE configs[2]); up to 64 share one pass over the rows
 constexpr int MAX_DEPTH = 16;                    // PRF depth upper bound (reference uses 10)
 
 // ---- order-preserving integer images of scores -------------------------------------------

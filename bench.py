@@ -2,7 +2,7 @@
 """bench.py - queries/sec of the query-time scoring path (BM25 + Doc2Vec dot + PRF re-rank + top-100)
 over a synthetic 10 M-doc index, on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--docs 10000000] [--batch 16] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--docs 10000000] [--batch 256] [--impl reference]
 
 A "step" is ONE batch of `--batch` queries through the whole path (both passes over the doc vectors).
 N > 1 (launched with torch.distributed.run): the 10 M docs are sharded by document across the ranks
@@ -35,7 +35,7 @@ SEED = 20260101
 
 def scan_kernel_for(batch: int):
     """(kernel name, key into profiles/traffic.json) of the scan launch that dominates a batch of this size"""
-    left = min(batch, 128)
+    left = min(batch, 256)
     if left >= 33:
         return "scan_tc_kernel<64> (tcgen05 kind::tf32 3xTF32, 64 queries per pass)", "scan_tc64"
     if left >= 9:
@@ -181,10 +181,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--docs", type=int, default=10_000_000)
-    ap.add_argument("--batch", type=int, default=64, help="queries per engine batch (1..128); up to 64 share one pass over the doc vectors")
+    ap.add_argument("--batch", type=int, default=256,
+                    help="queries per engine batch (1..256; BASELINE configs[2]: 10 M docs, batches of 256 queries with PRF); "
+                         "up to 64 share one pass over the doc vectors")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-docs", type=int, default=100_000)
     ap.add_argument("--cpu-queries", type=int, default=12)
@@ -220,7 +222,7 @@ def main():
     # ---- stage the shard [lo, hi) of the synthetic index into HBM -----------------------------------
     t_build = time.perf_counter()
     lo, hi = shard.shard_bounds(args.docs, world, rank)
-    eng = E.SearchEngine(device=local_rank, max_batch=max(args.batch, 128) if args.sweep else args.batch)
+    eng = E.SearchEngine(device=local_rank, max_batch=max(args.batch, 256) if args.sweep else args.batch)
     rows = eng.rows_tensor(hi - lo)
     sh = synth_torch.generate_shard(lo, hi, rows, vocab=VOCAB, seed=SEED)
     idf, avgdl, df = synth_torch.global_stats(sh, args.docs)
@@ -317,7 +319,7 @@ def main():
         # other operating points of the same engine: batch 1 = single-query latency mode (both scans at the HBM
         # roofline), batch 4 = largest batch of the fp32 SIMT scan; --sweep adds the rest
         sweep = {}
-        for bb in ((1, 2, 4, 8, 16, 32, 64, 128) if args.sweep else (1, 4)):
+        for bb in ((1, 2, 4, 8, 16, 32, 64, 128, 256) if args.sweep else (1, 64)):
             if bb > eng.params.max_batch:
                 break
             run_steps(2, bb, 0)

@@ -155,7 +155,7 @@ def test_batched_queries_equal_single_queries():
         eng.close()
 
 
-@pytest.mark.parametrize("mb", [8, 16, 24, 32, 47, 64, 100])
+@pytest.mark.parametrize("mb", [8, 16, 24, 32, 47, 64, 100, 200])
 def test_tensor_core_scan_accuracy(mb):
     """index[vec] through the batched scans against the fp64 dot product, every doc of every query: fp32-level error.
     8/16: mma.sync 3xTF32 (scan.cuh); 17..32: tcgen05 32 queries per pass; > 32: tcgen05 64 per pass (scan_tc.cuh).
