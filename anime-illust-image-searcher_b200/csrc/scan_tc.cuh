@@ -374,7 +374,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
     } else {
         // ---------------- epilogue warps: TMEM -> registers -> sim[q][doc] ----------------
         // Lane = doc; warp w reads TMEM lanes 32 * (w % 4) .. and the query columns of half w / 4.  A tcgen05.ld round
-        // trip costs ~700 clocks while the MMAs keep TMEM busy (measured with the CTA timeline, scratch/tc_trace.py:
+        // trip costs ~700 clocks while the MMAs keep TMEM busy (measured with the CTA timeline, tools/tc_trace.py:
         // 8 dependent rounds per tile made the epilogue, 6000 clocks, the longest stage of the pipeline), so a warp
         // issues all the loads of 16 query columns at once - one or two rounds per tile.  Per (doc, query): the fp32
         // sum of the accumulators, one coalesced store (a warp writes 128 contiguous bytes of sim[q]) and one FMNMX
