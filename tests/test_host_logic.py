@@ -86,3 +86,34 @@ def test_builder_host_side_matches_reference_outputs(main_index):
     assert np.array_equal(ids, np.concatenate(ix.doc_tag_seq))
     idf = G.idf_table(ix.df, ix.n_docs)
     assert sorted(idf) == z["idf_terms"].tolist() and all(idf[t] == z["idf"][t] for t in idf)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the reference's CPU algorithm on a bounded sample) needs no GPU: one JSON line with
+    the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--cpu-sample-docs", "3000"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_names_the_scan_kernel_of_a_batch():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.scan_kernel_for(1)[1] == "scan_simt" and bench.scan_kernel_for(8)[1] == "scan_mma8"
+    assert bench.scan_kernel_for(9)[1] == "scan_tc32" and bench.scan_kernel_for(32)[1] == "scan_tc32"
+    assert bench.scan_kernel_for(33)[1] == "scan_tc64" and bench.scan_kernel_for(256)[1] == "scan_tc64"
+    traffic, src = bench.load_traffic("scan_tc64", 5_000_000)
+    assert src and abs(traffic - 14556012000 / 2) < 1e6       # scaled to the shard's rows
