@@ -117,3 +117,23 @@ def test_bench_names_the_scan_kernel_of_a_batch():
     assert bench.scan_kernel_for(33)[1] == "scan_tc64" and bench.scan_kernel_for(256)[1] == "scan_tc64"
     traffic, src = bench.load_traffic("scan_tc64", 5_000_000)
     assert src and abs(traffic - 14556012000 / 2) < 1e6       # scaled to the shard's rows
+
+
+def test_packed_query_records_match_the_c_struct():
+    """engine._pack_queries builds the ais_query array in one numpy buffer: same bytes as filling the ctypes structures."""
+    import ctypes as C
+    import numpy as np
+    import ais_b200  # noqa: F401
+    from ais_b200 import binding as B, engine as E
+    rng = np.random.default_rng(0)
+    qs = [E.Query(rng.standard_normal(300).astype(np.float32), np.arange(1 + i % 5, dtype=np.int32) + i,
+                  rng.standard_normal(1 + i % 5)) for i in range(37)]
+    packed = E._pack_queries(qs)
+    rec = packed._as_parameter_
+    assert C.sizeof(B.AisQuery) == 32 and packed.buf.shape == (37, 4)
+    for i, q in enumerate(qs):
+        assert rec[i].n_terms == len(q.term_ids)
+        assert C.addressof(rec[i].vec.contents) == q.vec.ctypes.data
+        assert C.addressof(rec[i].term_ids.contents) == q.term_ids.ctypes.data
+        assert C.addressof(rec[i].weights.contents) == q.weights.ctypes.data
+        assert rec[i].vec[299] == q.vec[299] and rec[i].weights[0] == q.weights[0]
