@@ -40,6 +40,7 @@ class AisStats(C.Structure):
         ("n_docs", C.c_int64), ("n_postings", C.c_int64), ("dim", C.c_int32), ("n_terms", C.c_int32),
         ("scan_launches", C.c_int64), ("scan_ms_total", C.c_double), ("kernel_launches", C.c_int64),
         ("fullsort_fallbacks", C.c_int64), ("bytes_device", C.c_int64), ("column_scan_launches", C.c_int64),
+        ("tiles_per_seg", C.c_int64),
     ]
 
 

@@ -143,16 +143,28 @@ struct ais_engine {
     // per-batch work
     int qt_cap = 0;
     int64_t ld = 0;
-    Buf sim, bm25, fin, rer, d_q, d_q2, d_qt, maxs_key, maxb_key, maxr_key, maxes_own, maxr_own;
+    Buf sim, scratch64, fin_ext, rer, d_q, d_q2, d_qt, maxs_key, maxb_key, maxr_key, maxes_own, maxr_own;
     Buf top_ids, top_scores, status, rows_own;
     Buf blk_keys, blk_ids, grp_keys, grp_ids, cand_keys, cand_ids, rest_keys, rest_ids, rest_count;
+    Buf p1_keys, p1_ids;  int p1_k = 0;       // this shard's pass-1 candidates [nq][p1_k] (the pass-2 threshold starts from them)
     Buf out_ids, out_scores, out_count, out_amb;
     Buf fs_keys, fs_ids, fs_count;
     Buf bm25_slices;
     int bm25_t_cap = 1;
     Buf q_nreq;                // [qt_cap] number of required terms per query
+    Buf q_idf;                 // [qt_cap][MAX_TERMS] idf of every query term
     Buf tile_hdr;              // [qt_cap][tile_ld][8] bitmap of the docs with a BM25 record (bm25.cuh)
-    Buf tile_max;  int64_t tile_ld = 0;       // [qt_cap][tile_ld] best key per 256-doc tile (select2.cuh)
+    Buf tile_off;              // [qt_cap][tile_ld] first record slot of the tile, relative to rec_base[q]
+    Buf rec_val, rec_pos;      // record pools: fp64 values / positions inside the tile
+    Buf rec_base, rec_cursor;  // [qt_cap] int64 pool offset of the query / uint32 slots handed out
+    int64_t* h_rec_base = nullptr;
+    std::vector<int64_t> h_post_ptr;          // host copy of post_ptr: sizes the record pool of a batch (sum of df per query)
+    Buf tile_max;  int64_t tile_ld = 0;       // [qt_cap][tile_ld] best combined key per 256-doc tile (select2.cuh)
+    Buf tile_max2;             // the same for the blend R of a dense re-query (pass 2)
+    Buf col_lo, col_hi;        // [tile_ld] extreme values of the cached column per tile (pass 2, column mode)
+    const double* cur_maxes = nullptr;        // device [nq][2] global maxima of the current batch (caller- or engine-owned)
+    bool ext_fin = false;      // current batch: combined scores were supplied (ais_rerank), not computed
+    bool bound_ok = false;     // current batch, pass 2: the tile upper bound on R is valid (column mode, weights >= 0)
     Buf seg_max, sel_thr, surv_count, surv_keys, surv_ids, gate, witness, last_keys, wit_table;
     uint64_t* h_last_keys = nullptr;
     int sel_k_cap = 0, out_topn_cap = 0;
@@ -165,11 +177,13 @@ struct ais_engine {
     int h_out_cap = 0;
 
     // stats
-    int64_t column_scan_launches = 0;
+    int64_t column_scan_launches = 0, last_tiles_per_seg = 0;
     Buf colbuf;                    // rows[.][col_comp] as a compact array (column mode of the PRF re-query)
     int col_comp = -1;  const void* col_rows_ptr = nullptr;  int64_t col_n = -1;
     bool rer_column = false;       // current batch: rer[q][d] = colbuf[d] * d_q2[q][col_comp], never materialised
     bool requery_dense = false;    // AIS_REQUERY_DENSE=1: always run the dense scan for the PRF re-query
+    int sel_deep = -1;             // AIS_SELECT_DEPTH: cap on the extra prefix length the select stages ask for (-1: none)
+    bool no_bound = false;         // AIS_NO_TILE_BOUND=1: pass 2 always streams (no per-tile upper bound on R)
     int64_t scan_launches = 0, kernel_launches = 0, fullsort_fallbacks = 0, bytes_device = 0;
     bool profiling = false;
     bool use_mma = true;       // >= 5 queries per pass: tensor-core scan (3xTF32); AIS_SCAN_SIMT=1 keeps the fp32 SIMT kernel
@@ -209,9 +223,15 @@ struct DeviceGuard {
 
 int next_pow2_int(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
-int sel_blocks(const ais_engine* e) {
+// blocks per query of the gated streaming select; bounded so that its candidate lists [q][G][k] stay below 2^25 entries
+int sel_blocks_cap(const ais_engine* e, int k) {
+    int64_t cap = (1LL << 25) / ((int64_t)(e->qt_cap > 0 ? e->qt_cap : 1) * k);
+    if (cap > 4LL * e->sm_count) cap = 4LL * e->sm_count;
+    return (int)(cap < 4 ? 4 : cap);
+}
+int sel_blocks(const ais_engine* e, int k) {
     int64_t g = (e->n() + SEL_MIN_CHUNK - 1) / SEL_MIN_CHUNK;
-    const int64_t cap = 4LL * e->sm_count;
+    const int64_t cap = sel_blocks_cap(e, k);
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -233,9 +253,9 @@ int ensure_work(ais_engine* e) {
     if (qt <= e->qt_cap && ld <= e->ld) return AIS_OK;
     const int q = qt > e->qt_cap ? qt : e->qt_cap;
     const int64_t l = ld > e->ld ? ld : e->ld;
+    // per doc and query only the fp32 dot score stays resident; the re-query scores (rer) exist only for a dense
+    // re-query and the combined scores are never stored (finals.cuh)
     TRY(dev_alloc(e, e->sim, (size_t)q * l * sizeof(float)));
-    TRY(dev_alloc(e, e->rer, (size_t)q * l * sizeof(float)));
-    TRY(dev_alloc(e, e->fin, (size_t)q * l * sizeof(double)));
     TRY(dev_alloc(e, e->d_q, (size_t)q * DIM * sizeof(float)));
     TRY(dev_alloc(e, e->d_q2, (size_t)q * DIM * sizeof(float)));
     TRY(dev_alloc(e, e->d_qt, (size_t)q * sizeof(QueryTerms)));
@@ -254,7 +274,14 @@ int ensure_work(ais_engine* e) {
     const int64_t tl = (l + SEL_TILE - 1) / SEL_TILE;
     TRY(dev_alloc(e, e->tile_max, (size_t)q * tl * sizeof(uint64_t)));
     TRY(dev_alloc(e, e->tile_hdr, (size_t)q * tl * 8 * sizeof(uint32_t)));
+    TRY(dev_alloc(e, e->tile_off, (size_t)q * tl * sizeof(uint32_t)));
     TRY(dev_alloc(e, e->q_nreq, (size_t)q * sizeof(int32_t)));
+    TRY(dev_alloc(e, e->q_idf, (size_t)q * MAX_TERMS * sizeof(double)));
+    TRY(dev_alloc(e, e->rec_base, (size_t)q * sizeof(int64_t)));
+    TRY(dev_alloc(e, e->rec_cursor, (size_t)q * sizeof(unsigned int)));
+    TRY(dev_alloc(e, e->col_lo, (size_t)tl * sizeof(float)));
+    TRY(dev_alloc(e, e->col_hi, (size_t)tl * sizeof(float)));
+    e->col_comp = -1;                  // the per-tile column extremes are re-derived with the cached column
     e->tile_ld = tl;
     TRY(dev_alloc(e, e->sel_thr, (size_t)q * sizeof(uint64_t)));
     TRY(dev_alloc(e, e->surv_count, (size_t)q * sizeof(int)));
@@ -265,7 +292,9 @@ int ensure_work(ais_engine* e) {
     TRY(dev_alloc(e, e->last_keys, (size_t)q * sizeof(uint64_t)));
     if (q > e->qt_cap) {
         if (e->h_q) { cudaFreeHost(e->h_q); cudaFreeHost(e->h_qt); cudaFreeHost(e->h_q2); cudaFreeHost(e->h_top_ids);
-                      cudaFreeHost(e->h_top_scores); cudaFreeHost(e->h_small); cudaFreeHost(e->h_last_keys); }
+                      cudaFreeHost(e->h_top_scores); cudaFreeHost(e->h_small); cudaFreeHost(e->h_last_keys);
+                      cudaFreeHost(e->h_rec_base); }
+        CK(cudaMallocHost((void**)&e->h_rec_base, (size_t)q * sizeof(int64_t)));
         CK(cudaMallocHost((void**)&e->h_q, (size_t)q * DIM * sizeof(float)));
         CK(cudaMallocHost((void**)&e->h_q2, (size_t)q * DIM * sizeof(float)));
         CK(cudaMallocHost((void**)&e->h_qt, (size_t)q * sizeof(QueryTerms)));
@@ -284,8 +313,8 @@ int ensure_work(ais_engine* e) {
 int ensure_sel(ais_engine* e, int k) {
     if (k <= e->sel_k_cap) return AIS_OK;
     const size_t q = (size_t)e->qt_cap;
-    const size_t G = (size_t)4 * e->sm_count;
-    const size_t ng = (size_t)merge_groups((int)G) + 64;
+    const size_t G = (size_t)sel_blocks_cap(e, k);
+    const size_t ng = (size_t)merge_groups((int)(4 * e->sm_count)) + 64;
     TRY(dev_alloc(e, e->blk_keys, q * G * k * sizeof(uint64_t)));
     TRY(dev_alloc(e, e->blk_ids, q * G * k * sizeof(int64_t)));
     TRY(dev_alloc(e, e->grp_keys, q * ng * k * sizeof(uint64_t)));
@@ -460,13 +489,20 @@ RerRef rer_ref(const ais_engine* e) {
     return {e->rer.as<float>(), e->ld, nullptr};
 }
 
-// column mode of the re-query: make sure colbuf holds column `comp` of the current rows (extracted once per index)
+// column mode of the re-query: make sure colbuf holds column `comp` of the current rows (extracted once per index),
+// together with its extreme values per 256-doc tile (the pass-2 collect bounds the blend R of a tile with them)
 int prepare_column(ais_engine* e, int comp) {
     TRY(dev_alloc(e, e->colbuf, (size_t)(e->n_vec > 0 ? e->n_vec : 1) * sizeof(float)));
     if (e->col_comp != comp || e->col_rows_ptr != e->rows.p || e->col_n != e->n_vec) {
         if (e->n_vec > 0) {
             extract_column_kernel<<<(unsigned)((e->n_vec + 255) / 256), 256, 0, e->stream>>>(e->rows.as<float>(), e->n_vec, comp,
                                                                                         e->colbuf.as<float>());
+            LAUNCHED(e);
+            const int64_t n_tiles = (e->n_vec + SEL_TILE - 1) / SEL_TILE;
+            int64_t blocks = (n_tiles + 7) / 8;
+            if (blocks > 8LL * e->sm_count) blocks = 8LL * e->sm_count;
+            column_bounds_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(e->colbuf.as<float>(), e->n_vec, n_tiles,
+                                                                         e->col_lo.as<float>(), e->col_hi.as<float>());
             LAUNCHED(e);
         }
         e->col_comp = comp; e->col_rows_ptr = e->rows.p; e->col_n = e->n_vec;
@@ -511,11 +547,12 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(scan_tc_kernel<32, 3, 1, 6, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(32, 6)));
     CK(cudaFuncSetAttribute(scan_tc_kernel<64, 2, 1, 4, 2, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64, 4)));
-    CK(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
     return AIS_OK;
 }
 
+// Query records -> pinned staging -> device.  Also sizes the BM25 record pool of the batch: a query leaves at most
+// min(sum of its terms' document frequencies, n) records (docs whose BM25 value is not the query's default).
 int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bool with_terms) {
     for (int i = 0; i < nq; ++i) {
         if (with_vec) {
@@ -527,7 +564,12 @@ int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bo
                 return fail(AIS_ERR_INVALID, "query %d: n_terms %d outside [0, %d]", i, qs[i].n_terms, MAX_TERMS);
             QueryTerms& t = e->h_qt[i];
             t.n_terms = qs[i].n_terms;
-            for (int j = 0; j < qs[i].n_terms; ++j) { t.term[j] = qs[i].term_ids[j]; t.weight[j] = qs[i].weights[j]; }
+            t.n_required = 0;
+            for (int j = 0; j < qs[i].n_terms; ++j) {
+                t.term[j] = qs[i].term_ids[j];
+                t.weight[j] = qs[i].weights[j];
+                t.n_required += qs[i].weights[j] > e->p.require_magic;        // webui.py:161 (1000 itself is NOT required)
+            }
         }
     }
     if (with_vec) {
@@ -535,9 +577,45 @@ int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bo
         for (int i = nq; i < padded; ++i) memset(e->h_q + (size_t)i * DIM, 0, DIM * sizeof(float));
         CK(cudaMemcpyAsync(e->d_q.p, e->h_q, (size_t)padded * DIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     }
-    if (with_terms)
+    if (with_terms) {
         CK(cudaMemcpyAsync(e->d_qt.p, e->h_qt, (size_t)nq * sizeof(QueryTerms), cudaMemcpyHostToDevice, e->stream));
+        int64_t total = 0;
+        const int64_t n = e->n_bm25 > 0 ? e->n_bm25 : 0;
+        for (int i = 0; i < nq; ++i) {
+            int64_t touched = 0;
+            for (int j = 0; j < qs[i].n_terms; ++j) {
+                const int32_t t = qs[i].term_ids[j];
+                if (t >= 0 && t < e->n_vocab) touched += e->h_post_ptr[(size_t)t + 1] - e->h_post_ptr[(size_t)t];
+            }
+            e->h_rec_base[i] = total;
+            total += touched < n ? touched : n;
+        }
+        TRY(dev_alloc(e, e->rec_val, (size_t)total * sizeof(double)));
+        TRY(dev_alloc(e, e->rec_pos, (size_t)total));
+        CK(cudaMemcpyAsync(e->rec_base.p, e->h_rec_base, (size_t)nq * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+    }
     return AIS_OK;
+}
+
+// where the combined scores of the current batch come from (finals.cuh)
+FinSrc fin_src(const ais_engine* e, const double* d_maxes) {
+    FinSrc S;
+    memset(&S, 0, sizeof(S));
+    S.fin_ext = e->ext_fin ? e->fin_ext.as<double>() : nullptr;
+    S.sim = e->sim.as<float>();
+    S.ld = e->ld;
+    S.tile_hdr = e->tile_hdr.as<uint32_t>();
+    S.tile_off = e->tile_off.as<uint32_t>();
+    S.tile_ld = e->tile_ld;
+    S.rec_val = e->rec_val.as<double>();
+    S.rec_pos = e->rec_pos.as<uint8_t>();
+    S.rec_base = e->rec_base.as<int64_t>();
+    S.maxes = d_maxes;
+    S.n_required = e->q_nreq.as<int32_t>();
+    S.wb = e->p.bm25_weight;
+    S.wd = (float)e->p.doc2vec_weight;
+    S.n = e->n();
+    return S;
 }
 
 Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
@@ -548,23 +626,26 @@ Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
     a.n_sub = n_sub;
     a.post_doc = e->post_doc.as<int32_t>();
     a.post_tf = e->has_tf ? e->post_tf.as<int32_t>() : nullptr;
-    a.idf = e->idf.as<double>();
     a.kd = e->kd.as<double>();
     a.g1 = e->g1.as<double>();
     a.n = e->n_bm25;
-    a.n_vocab = e->n_vocab;
     a.queries = e->d_qt.as<QueryTerms>();
+    a.q_idf = e->q_idf.as<double>();
     a.magic = e->p.require_magic;
     a.k1p1 = e->p.k1 + 1.0;
     a.ld = e->ld;
-    a.fin = e->fin.as<double>();
     a.tile_hdr = e->tile_hdr.as<uint32_t>();
+    a.tile_off = e->tile_off.as<uint32_t>();
+    a.rec_val = e->rec_val.as<double>();
+    a.rec_pos = e->rec_pos.as<uint8_t>();
+    a.rec_base = e->rec_base.as<int64_t>();
+    a.rec_cursor = e->rec_cursor.as<unsigned int>();
     a.tile_ld = e->tile_ld;
-    a.n_required = e->q_nreq.as<int32_t>();
     return a;
 }
 
-// phase 0 of the BM25 side: slice table + per-query maximum (dense scores only for the compute_bm25_scores seam)
+// the BM25 side of a batch: slice table, per-tile records, per-query maximum (dense scores only for the
+// compute_bm25_scores seam)
 int launch_bm25_max(ais_engine* e, int nq, double* dense_out) {
     if (e->n_bm25 <= 0) return AIS_OK;
     const int64_t n_sub = (e->n_bm25 + BM25_SUB - 1) / BM25_SUB;
@@ -573,37 +654,13 @@ int launch_bm25_max(ais_engine* e, int nq, double* dense_out) {
     e->bm25_t_cap = t_cap;
     TRY(dev_alloc(e, e->bm25_slices, (size_t)e->qt_cap * t_cap * (n_sub + 1) * sizeof(int64_t)));
     bm25_slices_kernel<<<dim3((unsigned)((n_sub + 1 + 127) / 128), (unsigned)(nq * t_cap)), 128, 0, e->stream>>>(
-        e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->n_vocab, e->d_qt.as<QueryTerms>(), t_cap, n_sub,
-        e->bm25_slices.as<int64_t>(), e->p.require_magic, e->q_nreq.as<int32_t>());
+        e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->n_vocab, e->d_qt.as<QueryTerms>(), e->idf.as<double>(), t_cap, n_sub,
+        e->bm25_slices.as<int64_t>(), e->q_nreq.as<int32_t>(), e->rec_cursor.as<unsigned int>(), e->q_idf.as<double>());
     LAUNCHED(e);
     Bm25Args a = bm25_args(e, n_sub);
     a.max_keys = e->maxb_key.as<uint64_t>();
     a.dense_out = dense_out;
     bm25_score_kernel<<<dim3((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq), BM25_THREADS, BM25_SMEM, e->stream>>>(a);
-    LAUNCHED(e);
-    return AIS_OK;
-}
-
-// phase 1: BM25 again (shared memory only), normalise, combine with the dot scores, store the combined scores and the
-// segment maxima the streaming select starts from.  Needs the slice table of launch_bm25_max for the same batch.
-int launch_bm25_combine(ais_engine* e, int nq, const double* d_maxes, int* n_seg_out) {
-    const int64_t n_sub = (e->n_bm25 + BM25_SUB - 1) / BM25_SUB;
-    int64_t segs = n_sub;
-    if (segs > SEG_MAX) segs = SEG_MAX;
-    *n_seg_out = (int)segs;
-    CK(cudaMemsetAsync(e->seg_max.p, 0, (size_t)nq * SEG_MAX * sizeof(uint64_t), e->stream));
-    if (e->n_bm25 <= 0) return AIS_OK;
-    Bm25Args a = bm25_args(e, n_sub);
-    a.sim = e->sim.as<float>();
-    a.fin = e->fin.as<double>();
-    a.maxes = d_maxes;
-    a.wb = e->p.bm25_weight;
-    a.wd = (float)e->p.doc2vec_weight;
-    a.seg_max = e->seg_max.as<uint64_t>();
-    a.seg_mod = (int)segs;
-    a.tile_max = e->tile_max.as<uint64_t>();
-    a.tile_ld = e->tile_ld;
-    bm25_combine_kernel<<<dim3((unsigned)((n_sub + BM25C_WARPS - 1) / BM25C_WARPS), (unsigned)nq), BM25C_THREADS, 0, e->stream>>>(a);
     LAUNCHED(e);
     return AIS_OK;
 }
@@ -632,72 +689,109 @@ int merge_lists(ais_engine* e, const uint64_t* keys, const int64_t* ids, int n_l
     return AIS_OK;
 }
 
-// Exact local top-k of one scoring stage -> out[nq][k] (sorted best first, KEY_EMPTY padded).
-//   mode 0: combine sim + bm25 (stores the combined scores), 1: stored combined scores, 2: PRF blend.
-// Fast path: segment maxima -> threshold -> collect -> sort (select2.cuh); the buffer-based kernels of
-// select.cuh follow, gated per query on the overflow flag the fast path raises.
-int local_select(ais_engine* e, int mode, int nq, const double* d_maxes, int k, uint64_t* d_keys, int64_t* d_ids) {
-    if (k < 1 || k > SEL_KMAX) return fail(AIS_ERR_INVALID, "k %d outside [1, %d]", k, SEL_KMAX);
-    TRY(ensure_sel(e, k));
-    const int64_t n = e->n();
+// everything the select kernels share for the current batch; pass2: the blend R with the re-query scores
+SelectArgs select_args(ais_engine* e, bool pass2) {
     SelectArgs a;
-    const RerRef rr = rer_ref(e);
-    a.sim = e->sim.as<float>(); a.fin = e->fin.as<double>(); a.rer = rr.base; a.rer_qstride = rr.qstride; a.rer_scale = rr.scale;
-    a.n = n; a.ld = e->ld; a.id_base = e->first_doc;
+    memset(&a, 0, sizeof(a));
+    a.S = fin_src(e, e->cur_maxes);
+    if (pass2) {
+        const RerRef rr = rer_ref(e);
+        a.rer = rr.base; a.rer_qstride = rr.qstride; a.rer_scale = rr.scale;
+    }
+    a.n = e->n();
+    a.id_base = e->first_doc;
     a.cp = combine_params(e);
-    a.maxes = d_maxes;
     a.seeds_all = e->top_ids.as<int64_t>();
-    a.depth = e->p.prf_depth;
-    a.mode = mode;
-    // segments = groups of whole tiles (modes 1, 2; the BM25 kernel of mode 0 interleaves its sub-tiles over the segments)
-    a.n_tiles = (n + SEL_TILE - 1) / SEL_TILE;
+    a.depth = pass2 ? e->p.prf_depth : 0;
+    // segments = groups of whole tiles
+    a.n_tiles = (a.n + SEL_TILE - 1) / SEL_TILE;
     const int64_t tiles_per_seg = a.n_tiles > 0 ? (a.n_tiles + SEG_MAX - 1) / SEG_MAX : 1;
-    const int64_t S = (a.n_tiles + tiles_per_seg - 1) / tiles_per_seg;
-    a.n_seg = (int)S;
-    a.seg_len = tiles_per_seg * SEL_TILE;
-    a.tile_max = e->tile_max.as<uint64_t>();
-    a.tile_ld = e->tile_ld;
+    a.tiles_per_seg = (int)tiles_per_seg;
+    a.n_seg = (int)((a.n_tiles + tiles_per_seg - 1) / tiles_per_seg);
+    e->last_tiles_per_seg = tiles_per_seg;
     a.seg_max = e->seg_max.as<uint64_t>();
-    a.max_all = mode == 2 ? e->maxr_key.as<uint64_t>() : nullptr;
+    a.tile_max = e->tile_max.as<uint64_t>();
+    a.col_lo = e->col_lo.as<float>();
+    a.col_hi = e->col_hi.as<float>();
+    a.max_all = pass2 ? e->maxr_key.as<uint64_t>() : nullptr;
     a.thr = e->sel_thr.as<uint64_t>();
     a.surv_count = e->surv_count.as<int>();
     a.surv_keys = e->surv_keys.as<uint64_t>();
     a.surv_ids = e->surv_ids.as<int64_t>();
     a.gate = e->gate.as<int>();
-    if (mode == 0) {
-        // pass 1: the BM25 tile kernel's second phase forms the combined scores and the segment maxima in one go
-        TRY(launch_bm25_combine(e, nq, d_maxes, &a.n_seg));
-    } else if (n > 0) {
-        const dim3 g1((unsigned)((S + SEG_WARPS - 1) / SEG_WARPS), (unsigned)nq);
-        if (mode == 1) segmax_kernel<1><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
-        else segmax_kernel<2><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
+    return a;
+}
+
+// Exact local top-k of one scoring stage -> out[nq][k] (sorted best first, KEY_EMPTY padded).
+//   mode 0: pass 1 from the dot scores + BM25 records (bm25_combine_kernel emits the tile / segment maxima),
+//   mode 1: pass 1 from supplied combined scores (ais_rerank), 2: pass 2, the blend R.
+// Fast path: tile / segment maxima -> threshold -> collect -> sort (select2.cuh); the streaming buffer select
+// follows, gated per query on the overflow flag the fast path raises.
+int local_select(ais_engine* e, int mode, int nq, int k, uint64_t* d_keys, int64_t* d_ids) {
+    if (k < 1 || k > SEL_KMAX) return fail(AIS_ERR_INVALID, "k %d outside [1, %d]", k, SEL_KMAX);
+    TRY(ensure_sel(e, k));
+    const int64_t n = e->n();
+    SelectArgs a = select_args(e, mode == 2);
+    const bool bound = mode == 2 && e->bound_ok;         // pass 2: per-tile upper bound instead of a streaming pass
+    if (n > 0 && !bound) {
+        CK(cudaMemsetAsync(e->seg_max.p, 0, (size_t)nq * SEG_MAX * sizeof(uint64_t), e->stream));
+        if (mode == 0) {
+            CombineArgs c;
+            c.S = a.S;
+            c.n_sub = a.n_tiles;
+            c.seg_max = a.seg_max; c.seg_stride = SEG_MAX; c.tiles_per_seg = a.tiles_per_seg;
+            c.tile_max = a.tile_max;
+            bm25_combine_kernel<<<dim3((unsigned)((a.n_tiles + BM25C_WARPS - 1) / BM25C_WARPS), (unsigned)nq), BM25C_THREADS, 0, e->stream>>>(c);
+            LAUNCHED(e);
+        } else {
+            if (mode == 2) {                                 // the tile table of R is separate: pass 1's stays valid
+                TRY(dev_alloc(e, e->tile_max2, (size_t)e->qt_cap * e->tile_ld * sizeof(uint64_t)));
+                a.tile_max = e->tile_max2.as<uint64_t>();
+            }
+            const dim3 g1((unsigned)((a.n_seg + SEG_WARPS - 1) / SEG_WARPS), (unsigned)nq);
+            if (mode == 1) segmax_kernel<1><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
+            else segmax_kernel<2><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
+            LAUNCHED(e);
+        }
+    }
+    if (bound) {
+        rerank_threshold_kernel<<<nq, 256, 0, e->stream>>>(e->p1_keys.as<uint64_t>(), e->p1_ids.as<int64_t>(), e->p1_k, a, k);
+        LAUNCHED(e);
+    } else {
+        if (n <= 0) CK(cudaMemsetAsync(e->seg_max.p, 0, (size_t)nq * SEG_MAX * sizeof(uint64_t), e->stream));
+        threshold_kernel<<<nq, 256, 0, e->stream>>>(a.seg_max, a.n_seg, k, a.thr, a.surv_count, a.gate);
         LAUNCHED(e);
     }
-    threshold_kernel<<<nq, 256, 0, e->stream>>>(a.seg_max, a.n_seg, k, a.thr, a.surv_count, a.gate);
-    LAUNCHED(e);
     if (n > 0) {
         int64_t cb = (a.n_tiles + COLLECT_THREADS - 1) / COLLECT_THREADS;     // one lane per tile
         if (cb > 2LL * e->sm_count) cb = 2LL * e->sm_count;
         const dim3 g3((unsigned)cb, (unsigned)nq);
-        if (mode == 2) collect_kernel<2><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
-        else collect_kernel<1><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        if (mode != 2) collect_kernel<1, 0><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        else if (bound) collect_kernel<2, 1><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        else collect_kernel<2, 0><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
         LAUNCHED(e);
     }
     sort_survivors_kernel<<<nq, 512, SURV_CAP * 16, e->stream>>>(a.surv_count, a.surv_keys, a.surv_ids, k, d_keys, d_ids, a.gate);
     LAUNCHED(e);
     // gated fallback (runs only for queries whose survivors overflowed)
-    const int G = sel_blocks(e);
-    const int* gate = e->gate.as<int>();
-    if (mode == 0 || mode == 1)       // pass 1 has stored its combined scores by now
-        final_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(e->fin.as<double>(), n, e->ld, e->first_doc, k,
-                                                                       e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
-    else
-        rerank_select_kernel<<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(
-            e->fin.as<double>(), rr.base, rr.qstride, rr.scale, n, e->ld, a.cp, e->first_doc, e->top_ids.as<int64_t>(), e->p.prf_depth, k,
-            e->maxr_key.as<uint64_t>(), e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), gate);
+    const int G = sel_blocks(e, k);
+    if (mode != 2) stream_select_kernel<1><<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(a, k, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>());
+    else stream_select_kernel<2><<<dim3(G, nq), SEL_THREADS, 0, e->stream>>>(a, k, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>());
     LAUNCHED(e);
     return merge_lists(e, e->blk_keys.as<uint64_t>(), e->blk_ids.as<int64_t>(), G, k, (int64_t)G * k, k, k, nq, d_keys, d_ids,
-                       nullptr, gate);
+                       nullptr, e->gate.as<int>());
+}
+
+// combined scores of one query of the current batch -> e->scratch64 [n] (test seams only)
+int materialize_finals(ais_engine* e, int qi, const double* d_maxes) {
+    TRY(dev_alloc(e, e->scratch64, (size_t)e->ld * sizeof(double)));
+    if (e->n() == 0) return AIS_OK;
+    const int64_t n_tiles = (e->n() + SEL_TILE - 1) / SEL_TILE;
+    int64_t blocks = (n_tiles + 7) / 8;
+    if (blocks > 8LL * e->sm_count) blocks = 8LL * e->sm_count;
+    materialize_finals_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(fin_src(e, d_maxes), qi, n_tiles, e->scratch64.as<double>());
+    LAUNCHED(e);
+    return AIS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -716,12 +810,24 @@ int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
     e->cur_nq = nq;
     e->cur_prf = false;
     e->rer_column = false;
+    e->ext_fin = false;
+    e->bound_ok = false;
+    e->p1_k = 0;
     return AIS_OK;
 }
 
-// from_final: select straight from e->fin (ais_rerank); else combine sim + bm25 first
-int do_combine(ais_engine* e, int nq, const double* d_maxes, int k, uint64_t* d_keys, int64_t* d_ids, bool from_final) {
-    return local_select(e, from_final ? 1 : 0, nq, d_maxes, k, d_keys, d_ids);
+// pass 1: this shard's best k docs by combined score.  d_maxes: the GLOBAL maxima [nq][2] (must stay valid until the
+// batch is finished: the later stages recompute combined scores from them).  The list is also kept inside the engine:
+// the pass-2 threshold of the collapsed re-query starts from it.
+int do_combine(ais_engine* e, int nq, const double* d_maxes, int k, uint64_t* d_keys, int64_t* d_ids) {
+    e->cur_maxes = d_maxes;
+    TRY(local_select(e, e->ext_fin ? 1 : 0, nq, k, d_keys, d_ids));
+    TRY(dev_alloc(e, e->p1_keys, (size_t)e->qt_cap * SEL_KMAX * sizeof(uint64_t)));
+    TRY(dev_alloc(e, e->p1_ids, (size_t)e->qt_cap * SEL_KMAX * sizeof(int64_t)));
+    CK(cudaMemcpyAsync(e->p1_keys.p, d_keys, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->p1_ids.p, d_ids, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToDevice, e->stream));
+    e->p1_k = k;
+    return AIS_OK;
 }
 
 int do_top(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys, const int64_t* d_ids, int64_t* out_top_ids,
@@ -762,7 +868,7 @@ int do_top(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys, co
 
 int do_requery_select(ais_engine* e, int nq, int k, uint64_t* d_keys, int64_t* d_ids) {
     // the max is re-accumulated (idempotent under atomicMax)
-    return local_select(e, 2, nq, nullptr, k, d_keys, d_ids);
+    return local_select(e, 2, nq, k, d_keys, d_ids);
 }
 
 int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows, int prf_mode, int k, double* d_max_r,
@@ -802,8 +908,17 @@ int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows,
                                              e->maxr_key.as<uint64_t>(), e->status.as<int32_t>(), nq, 2);
     LAUNCHED(e);
     e->rer_column = comp >= 0;
-    if (comp >= 0) { TRY(prepare_column(e, comp)); e->column_scan_launches++; }      // no per-query array: col[d] * c_q on the fly
-    else TRY(launch_scan(e, e->d_q2.as<float>(), nq, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
+    if (comp >= 0) {                                     // no per-query array: col[d] * c_q on the fly
+        TRY(prepare_column(e, comp));
+        e->column_scan_launches++;
+    } else {                                             // dense re-query: the only case that holds a second score array
+        TRY(dev_alloc(e, e->rer, (size_t)e->qt_cap * e->ld * sizeof(float)));
+        TRY(launch_scan(e, e->d_q2.as<float>(), nq, e->rer.as<float>(), e->maxs_key.as<uint32_t>()));
+    }
+    // The per-tile bound on R (select2.cuh, collect_kernel<2, 1>) needs the column form, non-negative blend weights
+    // (every rounding of wo * fin + wr * (col * c) is then monotone) and this shard's pass-1 candidates.
+    e->bound_ok = comp >= 0 && !e->no_bound && e->p.original_score_weight > 0.0 && e->p.reranked_score_weight >= 0.0 &&
+                  e->p1_k > 0 && e->n() > 0;
     TRY(do_requery_select(e, nq, k, d_keys, d_ids));
     maxr_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxr_key.as<uint64_t>(), nq, d_max_r);
     LAUNCHED(e);
@@ -874,28 +989,22 @@ int do_witness(ais_engine* e, int nq, const int32_t* amb, const uint64_t* last_k
     for (int q = 0; q < nq; ++q) {
         if (!amb[q]) continue;
         CK(cudaMemsetAsync(e->wit_table.p, 0, (size_t)WITNESS_BUCKETS * sizeof(uint64_t), e->stream));
-        WitnessArgs a;
-        a.fin = e->fin.as<double>() + (size_t)q * e->ld;
-        const RerRef rr = rer_ref(e);
-        a.rer = rr.base + (size_t)q * rr.qstride;
-        a.rer_scale = rr.scale ? rr.scale + (size_t)q * DIM : nullptr;
-        a.n = e->n();
-        a.id_base = e->first_doc;
-        a.cp = combine_params(e);
-        a.second_pass = second_pass ? 1 : 0;
-        a.seeds = e->top_ids.as<int64_t>() + (size_t)q * MAX_DEPTH;
-        a.depth = e->p.prf_depth;
-        a.last_key = last_keys[q];
-        a.max_r = d_max_r ? d_max_r + q : nullptr;
-        a.normalize = d_max_r ? 1 : 0;
-        a.thresh = e->p.diff_filter_thresh;
-        a.inv_thresh = 1.0 / e->p.diff_filter_thresh;
-        a.table = e->wit_table.as<uint64_t>();
-        a.n_buckets = WITNESS_BUCKETS;
-        a.flag = d_witness + q;
-        int64_t blocks = (e->n() + 256 * 8 - 1) / (256 * 8);
+        WitnessArgs w;
+        w.a = select_args(e, second_pass != 0);
+        w.a.depth = second_pass ? e->p.prf_depth : 0;
+        w.qi = q;
+        w.second_pass = second_pass ? 1 : 0;
+        w.last_key = last_keys[q];
+        w.max_r = d_max_r ? d_max_r + q : nullptr;
+        w.normalize = d_max_r ? 1 : 0;
+        w.thresh = e->p.diff_filter_thresh;
+        w.inv_thresh = 1.0 / e->p.diff_filter_thresh;
+        w.table = e->wit_table.as<uint64_t>();
+        w.n_buckets = WITNESS_BUCKETS;
+        w.flag = d_witness + q;
+        int64_t blocks = (w.a.n_tiles + 7) / 8;
         if (blocks > 8LL * e->sm_count) blocks = 8LL * e->sm_count;
-        witness_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(a);
+        witness_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(w);
         LAUNCHED(e);
     }
     return AIS_OK;
@@ -926,12 +1035,10 @@ int bitonic_sort(ais_engine* e, uint64_t* keys, int64_t* ids, int64_t n_pad) {
 // write this shard's keys of query qi (pass 2: R, seeds blanked; pass 1: finals) into caller arrays [n_local]
 int do_export_keys(ais_engine* e, int qi, int second_pass, uint64_t* d_keys, int64_t* d_ids) {
     if (e->n() == 0) return AIS_OK;
-    const RerRef rr = rer_ref(e);
-    fill_keys_kernel<<<(unsigned)((e->n() + 255) / 256), 256, 0, e->stream>>>(
-        e->fin.as<double>() + (size_t)qi * e->ld, rr.base + (size_t)qi * rr.qstride, rr.scale ? rr.scale + (size_t)qi * DIM : nullptr,
-        e->n(), combine_params(e),
-        second_pass ? 1 : 0, e->first_doc, e->top_ids.as<int64_t>() + (size_t)qi * MAX_DEPTH, second_pass ? e->p.prf_depth : 0,
-        d_keys, d_ids, e->n());
+    SelectArgs a = select_args(e, second_pass != 0);
+    int64_t blocks = (a.n_tiles + 7) / 8;
+    if (blocks > 8LL * e->sm_count) blocks = 8LL * e->sm_count;
+    fill_keys_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>(a, qi, second_pass ? 1 : 0, d_keys, d_ids);
     LAUNCHED(e);
     return AIS_OK;
 }
@@ -991,36 +1098,58 @@ double np_sum_host(const double* a, int n) {
     return res;
 }
 
-// One batch on one GPU.  qs == NULL: finals are already in e->fin (ais_rerank).
+// How many candidates a select stage asks for.  The stages NEED `need` (topn + 1: the filter looks one entry past the
+// cut), but a longer exact prefix costs next to nothing (a few hundred more tiles recomputed, a larger survivor sort) and
+// lets tail_kernel see the second near-tie of filter_searched_result (webui.py:66-77) inside the prefix instead of
+// sending the query to the witness pass: at 10 M docs the best 1 024 scores hold ~10 gaps below 1e-6.  `cap`: the longest
+// list the stage may return.  Kept below half the segment count so that the segment-maximum threshold stays selective.
+int select_depth(const ais_engine* e, int need, int cap) {
+    const int64_t n_tiles = (e->n() + SEL_TILE - 1) / SEL_TILE;
+    const int64_t tps = n_tiles > 0 ? (n_tiles + SEG_MAX - 1) / SEG_MAX : 1;
+    const int64_t n_seg = (n_tiles + tps - 1) / tps;
+    int64_t deep = n_seg / 2;
+    if (e->sel_deep >= 0 && deep > e->sel_deep) deep = e->sel_deep;
+    int k = need > deep ? need : (int)deep;
+    if (k > cap) k = cap;
+    return k < 1 ? 1 : k;
+}
+
+// One batch on one GPU.  qs == NULL: the combined scores were supplied (ais_rerank, e->fin_ext).
 int run_batch(ais_engine* e, const ais_query* qs, int q_index0, int nq, int topn, int prf_mode, ais_infer_cb cb, void* ctx,
               int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status) {
     const int depth = e->p.prf_depth;
     TRY(check_loaded(e));
     TRY(ensure_work(e));            // every buffer exists BEFORE its pointer is taken
+    TRY(ensure_sel(e, SEL_KMAX));
     double* maxes = e->maxes_own.as<double>();
     if (qs) TRY(do_score(e, qs, nq, maxes));
     const bool prf = prf_mode != AIS_PRF_OFF && e->total() > depth;     // webui.py:193 `len(sims) > 10`
     std::vector<int32_t> amb(nq, 0), status(nq, 0);
-    {   // size the candidate buffers BEFORE their pointers are taken below
-        int kk = topn + 1 < SEL_KMAX ? topn + 1 : SEL_KMAX;
-        if (kk < depth) kk = depth;
-        TRY(ensure_sel(e, kk));
-    }
-
     std::vector<uint64_t> last_keys(nq, 0);
     auto any_amb = [&]() { bool any = false; for (int q = 0; q < nq; ++q) any = any || amb[q]; return any; };
+    uint64_t* ck = e->cand_keys.as<uint64_t>();
+    int64_t* ci = e->cand_ids.as<int64_t>();
+    // a result longer than the selector can return: the exact full-sort path below serves every query
+    const bool too_long = prf ? (topn + 1 - depth > SEL_KMAX - depth) : (topn + 1 > SEL_KMAX);
     if (!prf) {
-        const int k = topn + 1 < SEL_KMAX ? topn + 1 : SEL_KMAX;
-        TRY(do_combine(e, nq, maxes, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), qs == nullptr));
-        TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), nullptr, nullptr, topn, out_ids,
-                      out_scores, out_counts, out_status, amb.data(), last_keys.data()));
-        if (any_amb()) {       // one near-tie inside the prefix: look for a second one anywhere below it
-            TRY(do_witness(e, nq, amb.data(), last_keys.data(), 0, nullptr, e->witness.as<int32_t>()));
-            TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), nullptr, e->witness.as<int32_t>(),
-                          topn, out_ids, out_scores, out_counts, out_status, amb.data(), nullptr));
+        const int k = too_long ? 1 : select_depth(e, topn + 1, SEL_KMAX);
+        TRY(do_combine(e, nq, maxes, k, ck, ci));
+        if (!too_long) {
+            TRY(do_finish(e, nq, 1, k, ck, ci, nullptr, nullptr, topn, out_ids, out_scores, out_counts, out_status, amb.data(),
+                          last_keys.data()));
+            if (any_amb()) {       // one near-tie inside the prefix: look for a second one anywhere below it
+                TRY(do_witness(e, nq, amb.data(), last_keys.data(), 0, nullptr, e->witness.as<int32_t>()));
+                TRY(do_finish(e, nq, 1, k, ck, ci, nullptr, e->witness.as<int32_t>(), topn, out_ids, out_scores, out_counts,
+                              out_status, amb.data(), nullptr));
+            }
         }
     } else {
-        TRY(do_combine(e, nq, maxes, depth, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), qs == nullptr));
+        // pass 2 returns k2 docs next to the `depth` pinned seeds; pass 1 returns the seeds and as many docs again
+        // (the pass-2 threshold of the collapsed re-query is the k2-th best blend among them)
+        int k2 = topn + 1 - depth;
+        k2 = too_long ? SEL_KMAX - depth : select_depth(e, k2 < 1 ? 1 : k2, SEL_KMAX - depth);
+        const int k1 = depth + k2;
+        TRY(do_combine(e, nq, maxes, k1, ck, ci));
         const bool host_q2 = prf_mode == AIS_PRF_CALLBACK;
         std::vector<int64_t> top_ids;
         std::vector<double> top_scores;
@@ -1031,8 +1160,8 @@ int run_batch(ais_engine* e, const ais_query* qs, int q_index0, int nq, int topn
             top_scores.resize((size_t)nq * depth);
             q2.assign((size_t)nq * DIM, 0.0f);
         }
-        TRY(do_top(e, nq, 1, depth, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), host_q2 ? top_ids.data() : nullptr,
-                   host_q2 ? top_scores.data() : nullptr, host_q2 ? nullptr : e->rows_own.as<float>()));
+        TRY(do_top(e, nq, 1, k1, ck, ci, host_q2 ? top_ids.data() : nullptr, host_q2 ? top_scores.data() : nullptr,
+                   host_q2 ? nullptr : e->rows_own.as<float>()));
         if (host_q2) {
             bool any_bad = false;
             for (int q = 0; q < nq; ++q) {
@@ -1050,21 +1179,24 @@ int run_batch(ais_engine* e, const ais_query* qs, int q_index0, int nq, int topn
             if (any_bad)
                 CK(cudaMemcpyAsync(e->status.p, status.data(), (size_t)nq * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
         }
-        int k = topn + 1 - depth;
-        if (k < 1) k = 1;
-        if (k > SEL_KMAX) k = SEL_KMAX;
         double* maxr = e->maxr_own.as<double>();
-        TRY(do_requery(e, nq, host_q2 ? q2.data() : nullptr, host_q2 ? nullptr : e->rows_own.as<float>(), prf_mode, k, maxr,
-                       e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>()));
-        TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), maxr, nullptr, topn, out_ids, out_scores,
-                      out_counts, out_status, amb.data(), last_keys.data()));
-        if (any_amb()) {
-            TRY(do_witness(e, nq, amb.data(), last_keys.data(), 1, maxr, e->witness.as<int32_t>()));
-            TRY(do_finish(e, nq, 1, k, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), maxr, e->witness.as<int32_t>(), topn,
-                          out_ids, out_scores, out_counts, out_status, amb.data(), nullptr));
+        TRY(do_requery(e, nq, host_q2 ? q2.data() : nullptr, host_q2 ? nullptr : e->rows_own.as<float>(), prf_mode, k2, maxr, ck, ci));
+        if (!too_long) {
+            TRY(do_finish(e, nq, 1, k2, ck, ci, maxr, nullptr, topn, out_ids, out_scores, out_counts, out_status, amb.data(),
+                          last_keys.data()));
+            if (any_amb()) {
+                TRY(do_witness(e, nq, amb.data(), last_keys.data(), 1, maxr, e->witness.as<int32_t>()));
+                TRY(do_finish(e, nq, 1, k2, ck, ci, maxr, e->witness.as<int32_t>(), topn, out_ids, out_scores, out_counts,
+                              out_status, amb.data(), nullptr));
+            }
         }
     }
-    // exact fallback: the filter outcome depends on scores beyond the SEL_KMAX best -> sort everything
+    if (too_long) {
+        TRY(ensure_out(e, topn));
+        for (int q = 0; q < nq; ++q) amb[q] = 1;
+    }
+    // exact fallback: the filter outcome depends on scores beyond the selected prefix (or topn exceeds what the selector
+    // returns) -> sort every doc's key
     for (int q = 0; q < nq; ++q) {
         if (!amb[q]) continue;
         const int64_t cap = sort_capacity(e->n());
@@ -1144,6 +1276,8 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
     if (const char* tcm = getenv("AIS_SCAN_TC_MIN")) e->tc_min = atoi(tcm);
     if (const char* tcw = getenv("AIS_SCAN_TC_WIDE")) e->tc_wide = atoi(tcw) != 0;
     if (const char* rd = getenv("AIS_REQUERY_DENSE")) e->requery_dense = atoi(rd) != 0;
+    if (const char* nb = getenv("AIS_NO_TILE_BOUND")) e->no_bound = atoi(nb) != 0;
+    if (const char* sd = getenv("AIS_SELECT_DEPTH")) e->sel_deep = atoi(sd);
     int s = set_scan_attrs();
     if (s != AIS_OK) { cudaStreamDestroy(e->own_stream); delete e; return s; }
     *out = e;
@@ -1154,7 +1288,7 @@ int ais_destroy(ais_engine* e) {
     if (!e) return AIS_OK;
     DeviceGuard g(e->device);
     cudaStreamSynchronize(e->stream);
-    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->g1, &e->doc_len, &e->sim, &e->bm25, &e->fin,
+    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->g1, &e->doc_len, &e->sim, &e->scratch64, &e->fin_ext, &e->p1_keys, &e->p1_ids, &e->q_idf, &e->tile_off, &e->rec_val, &e->rec_pos, &e->rec_base, &e->rec_cursor, &e->tile_max2, &e->col_lo, &e->col_hi,
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
@@ -1162,7 +1296,7 @@ int ais_destroy(ais_engine* e) {
                    &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices, &e->qsplit})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,
-                    (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small, (void*)e->h_last_keys})
+                    (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small, (void*)e->h_last_keys, (void*)e->h_rec_base})
         if (h) cudaFreeHost(h);
     for (cudaEvent_t ev : e->ev_pending) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_free) cudaEventDestroy(ev);
@@ -1250,9 +1384,13 @@ int ais_load_bm25(ais_engine* e, const int64_t* post_ptr, const int32_t* post_do
     DeviceGuard g(e->device);
     TRY(dev_alloc(e, e->post_ptr, (size_t)(n_terms + 1) * sizeof(int64_t)));
     CK(cudaMemcpyAsync(e->post_ptr.p, post_ptr, (size_t)(n_terms + 1) * sizeof(int64_t), cudaMemcpyDefault, e->stream));
-    int64_t n_post = 0;
-    CK(cudaMemcpyAsync(&n_post, (const char*)e->post_ptr.p + (size_t)n_terms * sizeof(int64_t), sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    e->h_post_ptr.assign((size_t)n_terms + 1, 0);
+    CK(cudaMemcpyAsync(e->h_post_ptr.data(), e->post_ptr.p, (size_t)(n_terms + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    const int64_t n_post = e->h_post_ptr[(size_t)n_terms];
+    for (int32_t t = 0; t < n_terms; ++t)
+        if (e->h_post_ptr[(size_t)t + 1] < e->h_post_ptr[(size_t)t]) return fail(AIS_ERR_INVALID, "post_ptr is not monotonic at term %d", t);
+    if (e->h_post_ptr[0] != 0) return fail(AIS_ERR_INVALID, "post_ptr[0] must be 0");
     if (n_post < 0) return fail(AIS_ERR_INVALID, "post_ptr[n_terms] is negative");
     if (n_post > 0 && !post_doc) return fail(AIS_ERR_INVALID, "post_doc is NULL");
     TRY(dev_alloc(e, e->post_doc, (size_t)n_post * sizeof(int32_t)));
@@ -1366,6 +1504,8 @@ int ais_finish_bm25(ais_engine* e, const double* idf, double avgdl) {
                                                                           e->g1.as<double>());
         LAUNCHED(e);
     }
+    e->h_post_ptr.assign((size_t)e->n_vocab + 1, 0);
+    CK(cudaMemcpyAsync(e->h_post_ptr.data(), e->post_ptr.p, (size_t)(e->n_vocab + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->avgdl = avgdl;
     e->n_bm25 = n_docs;
@@ -1413,9 +1553,9 @@ int ais_bm25_scores(ais_engine* e, const int32_t* term_ids, const double* weight
     init_keys_kernel<<<1, 64, 0, e->stream>>>(e->maxs_key.as<uint32_t>(), e->maxb_key.as<uint64_t>(), e->maxr_key.as<uint64_t>(),
                                              e->status.as<int32_t>(), 1, 1);
     LAUNCHED(e);
-    TRY(dev_alloc(e, e->bm25, (size_t)e->ld * sizeof(double)));
-    TRY(launch_bm25_max(e, 1, e->bm25.as<double>()));
-    CK(cudaMemcpyAsync(out, e->bm25.p, (size_t)e->n_bm25 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    TRY(dev_alloc(e, e->scratch64, (size_t)e->ld * sizeof(double)));
+    TRY(launch_bm25_max(e, 1, e->scratch64.as<double>()));
+    CK(cudaMemcpyAsync(out, e->scratch64.p, (size_t)e->n_bm25 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return AIS_OK;
 }
@@ -1427,8 +1567,9 @@ int ais_final_scores(ais_engine* e, const ais_query* q, double* out) {
     TRY(ensure_work(e));
     TRY(ensure_sel(e, 1));
     TRY(do_score(e, q, 1, e->maxes_own.as<double>()));
-    TRY(do_combine(e, 1, e->maxes_own.as<double>(), 1, e->cand_keys.as<uint64_t>(), e->cand_ids.as<int64_t>(), false));
-    CK(cudaMemcpyAsync(out, e->fin.p, (size_t)e->n() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    e->cur_maxes = e->maxes_own.as<double>();
+    TRY(materialize_finals(e, 0, e->maxes_own.as<double>()));
+    CK(cudaMemcpyAsync(out, e->scratch64.p, (size_t)e->n() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return AIS_OK;
 }
@@ -1459,7 +1600,12 @@ int ais_rerank(ais_engine* e, const double* final_scores, int32_t topn, int32_t 
     TRY(check_loaded(e));
     TRY(need_whole_index(e));
     TRY(ensure_work(e));
-    CK(cudaMemcpyAsync(e->fin.p, final_scores, (size_t)e->n() * sizeof(double), cudaMemcpyDefault, e->stream));
+    TRY(dev_alloc(e, e->fin_ext, (size_t)e->ld * sizeof(double)));
+    CK(cudaMemcpyAsync(e->fin_ext.p, final_scores, (size_t)e->n() * sizeof(double), cudaMemcpyDefault, e->stream));
+    e->ext_fin = true;
+    e->rer_column = false;
+    e->bound_ok = false;
+    e->p1_k = 0;
     CK(cudaMemsetAsync(e->status.p, 0, sizeof(int32_t), e->stream));
     e->cur_nq = 1;
     return run_batch(e, nullptr, 0, 1, topn, prf_mode, cb, cb_ctx, out_ids, out_scores, out_count, out_status);
@@ -1527,7 +1673,7 @@ int ais_stage_combine(ais_engine* e, int32_t nq, const double* d_maxes, int32_t 
     if (!e || !d_maxes || !d_cand_keys || !d_cand_ids) return fail(AIS_ERR_INVALID, "NULL argument");
     if (nq != e->cur_nq) return fail(AIS_ERR_INVALID, "nq %d differs from the scored batch (%d)", nq, e->cur_nq);
     DeviceGuard g(e->device);
-    return do_combine(e, nq, d_maxes, k, d_cand_keys, d_cand_ids, false);
+    return do_combine(e, nq, d_maxes, k, d_cand_keys, d_cand_ids);
 }
 int ais_stage_top(ais_engine* e, int32_t nq, int32_t n_lists, int32_t k, const uint64_t* d_cand_keys, const int64_t* d_cand_ids,
                   int64_t* out_top_ids, double* out_top_scores, float* d_rows) {
@@ -1593,9 +1739,12 @@ int ais_debug_read(ais_engine* e, int32_t which, int32_t query, void* out) {
     if (which == 3 && e->rer_column && e->n_vec > 0)        // column mode keeps no rer array: materialise this query's row
         TRY(launch_scan_column(e, e->d_q2.as<float>() + (size_t)query * DIM, 1, e->col_comp, e->rer.as<float>() + (size_t)query * e->ld,
                                e->maxs_key.as<uint32_t>() + query));
+    if (which == 2) {
+        if (!e->cur_maxes) return fail(AIS_ERR_INVALID, "no combined scores: no batch has been combined yet");
+        TRY(materialize_finals(e, query, e->cur_maxes));
+    }
     const void* src = which == 0 ? (const void*)(e->sim.as<float>() + (size_t)query * e->ld)
-                    : which == 1 ? (const void*)(e->bm25.as<double>())
-                    : which == 2 ? (const void*)(e->fin.as<double>() + (size_t)query * e->ld)
+                    : (which == 1 || which == 2) ? (const void*)(e->scratch64.as<double>())
                                  : (const void*)(e->rer.as<float>() + (size_t)query * e->ld);
     CK(cudaMemcpyAsync(out, src, n * ((which == 0 || which == 3) ? 4 : 8), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1644,6 +1793,7 @@ int ais_get_stats(ais_engine* e, ais_stats* out) {
     out->fullsort_fallbacks = e->fullsort_fallbacks;
     out->bytes_device = e->bytes_device;
     out->column_scan_launches = e->column_scan_launches;
+    out->tiles_per_seg = e->last_tiles_per_seg;
     return AIS_OK;
 }
 int ais_reset_stats(ais_engine* e) {

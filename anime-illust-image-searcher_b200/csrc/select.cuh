@@ -149,85 +149,6 @@ struct CombineParams {
     float wr;    // RERANKED_SCORE_WEIGHT (fp32 multiply, same reason)
 };
 
-// select straight from stored final scores (no-PRF branch webui.py:247-253 and ais_rerank)
-struct FinalF {
-    const double* fin;
-    int64_t id_base;
-    __device__ __forceinline__ bool operator()(int64_t i, uint64_t& key, int64_t& id) const {
-        key = dkey(fin[i]);
-        id = id_base + i;
-        return true;
-    }
-};
-__global__ void __launch_bounds__(SEL_THREADS)
-final_select_kernel(const double* __restrict__ fin, int64_t n, int64_t ld, int64_t id_base, int k,
-                    uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids, const int* __restrict__ gate) {
-    __shared__ SelBuf sb;
-    const int qi = blockIdx.y;
-    if (gate && !gate[qi]) return;
-    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * chunk;
-    const int64_t hi = lo + chunk < n ? lo + chunk : n;
-    sel_init(sb);
-    FinalF f{fin + qi * ld, id_base};
-    if (lo < hi) sel_stream(sb, lo, hi, k, f);
-    else { __syncthreads(); sel_prune(sb, k); }
-    const size_t o = ((size_t)qi * gridDim.x + blockIdx.x) * (size_t)k;
-    sel_write(sb, k, cand_keys + o, cand_ids + o);
-}
-
-// ---- pass 2: R = 0.7*final + 0.3*rer (webui.py:208), its max, local top-k without the top docs ----
-// The re-query scores of a query are either a row of the materialised `rer` array (scale 1) or - column mode, the
-// reference's collapsed PRF centroid [c, 0, ..., 0] - the shared column rows[.][0] times the query's scalar c:
-// rer[i] = RN(p[i] * cq) in both cases (x * 1 = x exactly).
-struct RerankF {
-    const double* fin;
-    const float* rer;
-    float cq;
-    CombineParams cp;
-    int64_t id_base;
-    const int64_t* top_ids;   // shared memory
-    int depth;
-    uint64_t* best;           // thread-local running max key
-    __device__ __forceinline__ bool operator()(int64_t i, uint64_t& key, int64_t& id) const {
-        const float hr = __fmul_rn(cp.wr, __fmul_rn(rer[i], cq));
-        const double r = __dadd_rn(__dmul_rn(cp.wo, fin[i]), (double)hr);
-        key = dkey(r);
-        id = id_base + i;
-        *best = key > *best ? key : *best;      // max over ALL docs, top docs and masked ones included
-        bool keep = true;
-        for (int t = 0; t < depth; ++t) keep = keep && (top_ids[t] != id);   // webui.py:217
-        return keep;
-    }
-};
-
-// mode 0: write candidates [nq][grid][k];  mode 1: no selection, only the max (used before a full sort)
-__global__ void __launch_bounds__(SEL_THREADS)
-rerank_select_kernel(const double* __restrict__ fin, const float* __restrict__ rer, int64_t rer_qstride,
-                     const float* __restrict__ rer_scale /* null: 1; else [q * DIM] */, int64_t n, int64_t ld,
-                     CombineParams cp, int64_t id_base, const int64_t* __restrict__ top_ids_all, int depth, int k,
-                     uint64_t* __restrict__ max_keys, uint64_t* __restrict__ cand_keys, int64_t* __restrict__ cand_ids,
-                     const int* __restrict__ gate) {
-    __shared__ SelBuf sb;
-    __shared__ int64_t top_ids[MAX_DEPTH];
-    __shared__ uint64_t wscratch[SEL_THREADS / 32];
-    const int qi = blockIdx.y;
-    if (gate && !gate[qi]) return;
-    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * chunk;
-    const int64_t hi = lo + chunk < n ? lo + chunk : n;
-    if (threadIdx.x < depth) top_ids[threadIdx.x] = top_ids_all[qi * MAX_DEPTH + threadIdx.x];
-    sel_init(sb);
-    uint64_t best = dkey(-INFINITY);
-    RerankF f{fin + qi * ld, rer + qi * rer_qstride, rer_scale ? rer_scale[(size_t)qi * DIM] : 1.0f, cp, id_base, top_ids, depth, &best};
-    if (lo < hi) sel_stream(sb, lo, hi, k, f);
-    else { __syncthreads(); sel_prune(sb, k); }
-    const size_t o = ((size_t)qi * gridDim.x + blockIdx.x) * (size_t)k;
-    sel_write(sb, k, cand_keys + o, cand_ids + o);
-    __syncthreads();
-    block_max_to_global(best, wscratch, &max_keys[qi]);
-}
-
 // ---- merge candidate lists.  Entry (list, query, pos) sits at list*list_stride + query*q_stride + pos:
 //      all-gathered lists [n_lists][nq][k]: list_stride = nq*k, q_stride = k;
 //      a kernel's per-block lists [nq][grid][k]: list_stride = k, q_stride = grid*k.
@@ -464,26 +385,7 @@ tail_kernel(const uint64_t* __restrict__ rest_keys_all, const int64_t* __restric
     }
 }
 
-// ---- fallback: sort ALL second-pass keys of a shard (ambiguous filter outcome) -----------------
-__global__ void fill_keys_kernel(const double* __restrict__ fin, const float* __restrict__ rer,
-                                 const float* __restrict__ rer_scale /* null: 1 */, int64_t n, CombineParams cp, int use_rer, int64_t id_base, const int64_t* __restrict__ top_ids,
-                                 int depth, uint64_t* __restrict__ keys, int64_t* __restrict__ ids, int64_t n_pad) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pad) return;
-    uint64_t key = KEY_EMPTY;
-    int64_t id = ID_EMPTY;
-    if (i < n) {
-        double r = fin[i];
-        if (use_rer) r = __dadd_rn(__dmul_rn(cp.wo, r), (double)__fmul_rn(cp.wr, __fmul_rn(rer[i], rer_scale ? *rer_scale : 1.0f)));
-        key = dkey(r);
-        id = id_base + i;
-        for (int t = 0; t < depth; ++t)
-            if (top_ids[t] == id) { key = KEY_EMPTY; id = ID_EMPTY; }
-    }
-    keys[i] = key;
-    ids[i] = id;
-}
-
+// ---- fallback: sort ALL keys of a shard (ambiguous filter outcome; keys from fill_keys_kernel, select2.cuh) ----
 constexpr int GS_TILE = 2048;     // elements sorted per block in shared memory
 constexpr int GS_THREADS = 256;
 

@@ -83,6 +83,21 @@ class ShardedSearch:
         self.depth = int(self.engines[0].params.prf_depth)
         self.kmax = int(self.engines[0].max_select_k())
         self.fullsort_fallbacks = 0
+        self.n_shards = self.comm.world * len(self.engines)
+
+    def _select_depth(self, need: int, cap: int) -> int:
+        """Candidates a select stage asks for - the engine's own policy (engine.cu select_depth), from GLOBAL quantities so
+        that every rank gathers lists of the same length: a longer exact prefix is nearly free and lets the filter see its
+        second near-tie (webui.py:66-77) without the witness pass; kept below half a shard's segment count."""
+        import os
+        per = -(-self.n_total // max(1, self.n_shards))
+        n_tiles = -(-per // 256)
+        tps = max(1, -(-n_tiles // 2048))
+        deep = (-(-n_tiles // tps)) // 2
+        env = os.environ.get("AIS_SELECT_DEPTH")
+        if env is not None and int(env) >= 0:
+            deep = min(deep, int(env))
+        return max(1, min(cap, max(need, deep)))
 
     # ---- helpers ----------------------------------------------------------------------------------
     def _dev(self, eng):
@@ -128,20 +143,25 @@ class ShardedSearch:
         maxes_e = [maxes.to(self._dev(e)) for e in E]
         prf = prf_mode != PRF_OFF and self.n_total > depth
 
+        # a result longer than the selector returns: every query goes through the exact full sort (_resolve_ambiguous)
+        too_long = topn + 1 > self.kmax
         if not prf:
-            k = min(topn + 1, self.kmax)
+            k = 1 if too_long else self._select_depth(topn + 1, self.kmax)
             keys, ids = self._cand_buffers(nq, k)
             for e, m, kk, ii in zip(E, maxes_e, keys, ids):
                 e.stage_combine(nq, m, k, kk, ii)
             gk, gi = self._gather_lists(keys, ids)
-            res = self._finish(nq, k, gk, gi, None, topn, second_pass=False)
+            res = self._finish(nq, k, gk, gi, None, topn, second_pass=False, all_ambiguous=too_long)
             return self._resolve_ambiguous(res, nq, topn, None, second_pass=False) + (errors,)
 
-        # --- PRF seeds: global top-`depth`
-        keys, ids = self._cand_buffers(nq, depth)
+        # --- pass 1: every shard's best k1 = depth + k2 docs (the engine keeps the list: its pass-2 threshold starts from
+        # it); the global PRF seeds are the best `depth` of the shards' first `depth` entries
+        k2 = (self.kmax - depth) if too_long else self._select_depth(max(1, topn + 1 - depth), self.kmax - depth)
+        k1 = depth + k2
+        keys, ids = self._cand_buffers(nq, k1)
         for e, m, kk, ii in zip(E, maxes_e, keys, ids):
-            e.stage_combine(nq, m, depth, kk, ii)
-        gk, gi = self._gather_lists(keys, ids)
+            e.stage_combine(nq, m, k1, kk, ii)
+        gk, gi = self._gather_lists([kk[:, :depth].clone() for kk in keys], [ii[:, :depth].clone() for ii in ids])
         host = prf_mode == PRF_CALLBACK
         rows_l = None if host else [torch.empty((nq, depth, 300), dtype=torch.float32, device=self._dev(e)) for e in E]
         top = None
@@ -184,22 +204,24 @@ class ShardedSearch:
             rows_e = [rows.to(self._dev(e)) for e in E]
 
         # --- pass 2
-        k = max(1, min(topn + 1 - depth, self.kmax))
+        k = k2
         keys, ids = self._cand_buffers(nq, k)
         maxr_l = [torch.empty((nq,), dtype=torch.float64, device=self._dev(e)) for e in E]
         for e, r, mr, kk, ii in zip(E, rows_e, maxr_l, keys, ids):
             e.stage_requery(nq, q2, r, prf_mode, k, mr, kk, ii)
         maxr = self.comm.all_max(self._reduce_local(maxr_l, torch.maximum))
         gk, gi = self._gather_lists(keys, ids)
-        res = self._finish(nq, k, gk, gi, maxr, topn, second_pass=True)
+        res = self._finish(nq, k, gk, gi, maxr, topn, second_pass=True, all_ambiguous=too_long)
         return self._resolve_ambiguous(res, nq, topn, maxr, second_pass=True) + (errors,)
 
-    def _finish(self, nq: int, k: int, gk, gi, maxr, topn: int, second_pass: bool):
+    def _finish(self, nq: int, k: int, gk, gi, maxr, topn: int, second_pass: bool, all_ambiguous: bool = False):
         """stage_finish on engine 0 (every rank holds identical inputs); an ambiguous filter outcome first
         goes through the near-tie witness pass on every shard (flags all-reduced with MAX)."""
         E = self.engines
         res = E[0].stage_finish(nq, gk.shape[0], k, gk, gi, maxr, topn)
         amb, last = res[4], res[5]
+        if all_ambiguous:
+            return res[:4] + (np.ones(nq, dtype=np.int32),)
         if amb.any():
             flags = []
             for e in E:

@@ -103,6 +103,7 @@ typedef struct ais_stats {
     int64_t fullsort_fallbacks; /* times the ambiguous-filter fallback sorted the whole shard */
     int64_t bytes_device;       /* device memory held by the engine */
     int64_t column_scan_launches; /* re-query passes served by the single-component column scan */
+    int64_t tiles_per_seg;      /* 256-doc tiles per select segment in the last batch (> 1 from ~525 k docs per shard) */
 } ais_stats;
 
 const char* ais_last_error(void);

@@ -264,6 +264,53 @@ class OraclePort:
         final = self.combine(sims, bm25)
         return self.rerank(final, topn)
 
+    # ---- the same path without N-long Python lists (for >= 1 M docs) -------------
+    def rerank_arrays(self, final_scores: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """rerank_sorted (webui.py:189-237) as (doc ids, scores) ARRAYS: same arithmetic, same stable sorts, no tuples."""
+        n = len(final_scores)
+        order = np.argsort(-final_scores, kind="stable")
+        if n <= PRF_DEPTH:
+            return order, final_scores[order]
+        top_ids = order[:PRF_DEPTH]
+        vecs = [self.doc_vector_pairs(int(d) + 1) for d in top_ids]
+        q2 = self.prf_query(vecs, [final_scores[d] for d in top_ids])
+        rer = self.index[q2]
+        R = self.consts["ORIGINAL_SCORE_WEIGHT"] * final_scores + self.consts["RERANKED_SCORE_WEIGHT"] * rer
+        if R.max() > 0:
+            R = R / R.max()
+        ro = np.argsort(-R, kind="stable")
+        ro = ro[~np.isin(ro, top_ids)]
+        return np.concatenate([top_ids, ro]), np.concatenate([np.ones(PRF_DEPTH), R[ro]])
+
+    @staticmethod
+    def filter_arrays(ids: np.ndarray, s: np.ndarray, thresh: float, topn: int) -> List[Tuple[int, float]]:
+        """filter_searched_result (webui.py:63-80) + [:topn] (webui.py:243-246) on arrays."""
+        diff = s[:-1] - s[1:]
+        diff = np.where(diff == 0, np.inf, diff)
+        t = len(s)
+        found = np.where(diff < thresh)[0]
+        if len(found) == 1:
+            t = int(found[0])
+        elif len(found) >= 2:
+            t = int(found[1])
+        max_val = float(s.max())
+        keep = np.nonzero(s[:t] > 0)[0][:topn]           # `if score > 0` over range(t), then [:topn]: order kept
+        return [(int(ids[i]), s[i] / max_val) for i in keep]
+
+    def find_fast(self, new_doc: str, topn: int = 50) -> List[Tuple[int, float]]:
+        """find_similar_documents(new_doc, topn), bit-identical to the list-based path above (tests/test_oracle_golden.py)."""
+        vec = self.query_vector(new_doc)
+        sims = self.index[vec]
+        weights, _, _ = parse_query_weights(new_doc, self.token2id, self.consts["REQUIRE_TAG_MAGIC_NUMBER"])
+        ids, s = self.rerank_arrays(self.combine(sims, self.bm25_scores(weights)))
+        return self.filter_arrays(ids, s, self.consts["DIFF_FILTER_THRESH"], topn)
+
+    def find_sorted_arrays(self, new_doc: str) -> Tuple[np.ndarray, np.ndarray]:
+        vec = self.query_vector(new_doc)
+        sims = self.index[vec]
+        weights, _, _ = parse_query_weights(new_doc, self.token2id, self.consts["REQUIRE_TAG_MAGIC_NUMBER"])
+        return self.rerank_arrays(self.combine(sims, self.bm25_scores(weights)))
+
     # ---- intermediate products, for kernel-level parity tests -----------------
     def stages(self, new_doc: str) -> Dict[str, np.ndarray]:
         vec = self.query_vector(new_doc)

@@ -355,6 +355,62 @@ def test_filter_fallback_is_exact_and_counted():
             webui_api.RERANKED_SCORE_WEIGHT = 0.3
 
 
+@pytest.mark.parametrize("prf_mode", ["stored_rows", "off"])
+def test_topn_beyond_the_selector_is_not_truncated(prf_mode):
+    """find_similar_documents(new_doc, topn) accepts any topn (webui.py:345); the select stages return at most
+    ais_max_select_k() = 1024 candidates, so a longer result goes through the exact full sort of every doc's key -
+    single engine and doc-sharded - instead of being cut silently."""
+    from ais_b200 import shard
+    idx = synth.generate_index(30000, vocab_size=1500, seed=61)
+    P = port.OraclePort(idx)
+    t2i = idx.token2id
+    infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
+    texts = synth.generate_queries(idx, 5, seed=4)
+    eng = install(idx, prf_mode=prf_mode)
+    engines = [E.SearchEngine.from_index(idx, lo=lo, hi=hi) for lo, hi in (shard.shard_bounds(idx.n_docs, 2, r) for r in range(2))]
+    S = shard.ShardedSearch(engines, idx.n_docs)
+    mode = E.PRF_STORED_ROWS if prf_mode == "stored_rows" else E.PRF_OFF
+    n_long = 0
+    for text in texts:
+        for topn in (1100, 2500):
+            if prf_mode == "off":
+                st = P.stages(text)
+                order = np.argsort(-st["final"], kind="stable")
+                srt = list(zip(order.tolist(), st["final"][order]))
+                want = capture(lambda: port.filter_searched_result(srt)[:topn])
+                got = capture(lambda: eng.search([Q.make_query(text, t2i, infer)], topn, mode)[0])
+                sorted_fn = lambda s=srt: s
+            else:
+                want = capture(P.find_similar_documents, text, topn)
+                got = capture(webui_api.find_similar_documents, text, topn)
+                sorted_fn = lambda t=text: P.find_sorted(t)
+            assert_same_or_filter_unstable(got, want, sorted_fn, 1e-6, topn, (text, topn))
+            got2 = capture(lambda: S.search([Q.make_query(text, t2i, infer)], topn, mode)[0])
+            assert_same_or_filter_unstable(got2, want, sorted_fn, 1e-6, topn, ("sharded", text, topn))
+            n_long += want[0] == "ok" and len(want[1]) > 1034
+    assert n_long > 0, "no query returned more than the selector's 1024 + 10 docs: the test did not reach the long path"
+    for e in engines:
+        e.close()
+
+
+def test_pass2_tile_bound_equals_streaming_pass(monkeypatch):
+    """Pass 2 of the reference's collapsed re-query skips tiles by an upper bound on the blend R (select2.cuh,
+    collect_kernel<2, 1>); AIS_NO_TILE_BOUND=1 streams every doc instead.  Same results bit for bit, max R included."""
+    idx = synth.generate_index(60000, vocab_size=2000, seed=88)
+    t2i = idx.token2id
+    infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
+    qs = [Q.make_query(q, t2i, infer) for q in synth.generate_queries(idx, 24, seed=6)]
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("AIS_NO_TILE_BOUND", flag)
+        eng = E.SearchEngine.from_index(idx, max_batch=24)
+        out[flag] = [eng.search_raw(qs, topn, E.PRF_STORED_ROWS) for topn in (100, 800)]
+        eng.close()
+    for a, b in zip(out["0"], out["1"]):
+        for x, y in zip(a[:4], b[:4]):
+            assert np.array_equal(x, y)
+
+
 def test_clustered_top_docs_overflow_the_streaming_select():
     """All the best docs sit in one contiguous id range: the segment-maximum threshold lets thousands of
     survivors through, the streaming select overflows and the gated buffer select must take over."""

@@ -67,3 +67,27 @@ def test_port_matches_live_reference_on_fresh_index():
         a = run_and_capture(W.find_similar_documents, q, 100)
         b = run_and_capture(P.find_similar_documents, q, 100)
         assert a == b, q
+
+
+def test_array_flavour_of_the_port_is_bit_identical(main_index):
+    """find_fast (no N-long Python lists; what the >= 1 M-doc GPU tests and bench.py --verify compare with) returns exactly
+    what the reference returned - golden results incl. the exception types/messages - and what the list flavour returns on
+    fresh indexes (tf > 1, the N <= 10 branch, topn 5/100/800)."""
+    from ais_b200 import synth
+    P = port.OraclePort(main_index)
+    for rec in load_results("main")["results"]:
+        got = run_and_capture(P.find_fast, rec["query"], rec["topn"])
+        if "error" in rec:
+            assert got[0] == "err" and got[1] == rec["error"] and got[2] == rec["message"], (rec["query"], got)
+        else:
+            assert got == ("ok", rec["ids"], rec["scores"]), rec["query"]
+    Pt = port.OraclePort(load_index("tiny"))
+    for rec in load_results("tiny")["results"]:
+        assert run_and_capture(Pt.find_fast, rec["query"], rec["topn"]) == ("ok", rec["ids"], rec["scores"]), rec["query"]
+    ix = synth.generate_index(4000, vocab_size=300, seed=5, tf_gt1_fraction=0.02)
+    P2 = port.OraclePort(ix)
+    for thresh in (1e-6, 1e-4):                      # 1e-4: near-ties are common, the cut branches run
+        P2.consts["DIFF_FILTER_THRESH"] = thresh
+        for q in synth.generate_queries(ix, 30, seed=11):
+            for topn in (5, 100, 800):
+                assert run_and_capture(P2.find_fast, q, topn) == run_and_capture(P2.find_similar_documents, q, topn), (q, topn)
