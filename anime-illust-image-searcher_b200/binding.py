@@ -41,7 +41,11 @@ class AisStats(C.Structure):
         ("scan_launches", C.c_int64), ("scan_ms_total", C.c_double), ("kernel_launches", C.c_int64),
         ("fullsort_fallbacks", C.c_int64), ("bytes_device", C.c_int64), ("column_scan_launches", C.c_int64),
         ("tiles_per_seg", C.c_int64),
+        ("kind_ms", C.c_double * 8), ("kind_launches", C.c_int64 * 8), ("bound_passes", C.c_int64), ("bitmap_batches", C.c_int64),
     ]
+
+
+KIND_NAMES = ("scan", "bm25_slices", "bm25_score", "combine", "select", "requery", "tail", "witness")
 
 
 INFER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int32,
@@ -66,6 +70,9 @@ SIGNATURES = {
     "ais_build_bm25": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "ais_finish_bm25": (C.c_int, [_vp, _vp, _dbl]),
     "ais_export_postings": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "ais_pickle_csr_scan": (C.c_int, [C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "ais_pickle_csr_fill": (C.c_int, [C.c_char_p, _i64, _i64, _vp, _vp, _vp]),
+    "ais_pickle_last_error": (C.c_char_p, []),
     "ais_dot_scores": (C.c_int, [_vp, _vp, _vp]),
     "ais_bm25_scores": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "ais_final_scores": (C.c_int, [_vp, C.POINTER(AisQuery), _vp]),

@@ -26,12 +26,6 @@ constexpr int BM25_THREADS = 32 * BM25_WARPS;
 constexpr int BM25_WARP_SMEM = BM25_SUB * 8 + BM25_SUB;           // fp64 accumulators + required-term counters
 constexpr int BM25_SMEM = BM25_WARPS * BM25_WARP_SMEM;
 
-struct QueryTerms {  // device-resident, one per query of the batch
-    int32_t n_terms;
-    int32_t n_required;                          // terms with weight > REQUIRE_TAG_MAGIC_NUMBER (webui.py:161); host-filled
-    int32_t term[MAX_TERMS];
-    double weight[MAX_TERMS];
-};
 
 __global__ void kd_kernel(const int64_t* __restrict__ doc_len, int64_t n, double avgdl, double k1, double b,
                           double one_minus_b, double k1p1, double* __restrict__ kd, double* __restrict__ g1) {
@@ -46,20 +40,46 @@ __global__ void kd_kernel(const int64_t* __restrict__ doc_len, int64_t n, double
     g1[i] = __ddiv_rn(__dmul_rn(1.0, k1p1), __dadd_rn(1.0, k));
 }
 
+// K_d and the tf == 1 quotient depend on the doc only through its length: tables indexed by the length, and the length
+// of every posting's doc next to the posting (uint16), turn the score kernel's per-posting gather into the 80 MB per-doc
+// arrays into one coalesced 2-byte load plus an L1 hit.  Same operations as kd_kernel -> same bits.
+__global__ void max_len_kernel(const int64_t* __restrict__ doc_len, int64_t n, unsigned long long* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0ull;
+    if (i < n) v = doc_len[i] < 0 ? ~0ull : (unsigned long long)doc_len[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    if ((threadIdx.x & 31) == 0 && v > 0ull) atomicMax(out, v);
+}
+__global__ void kd_table_kernel(int64_t max_len, double avgdl, double k1, double b, double one_minus_b, double k1p1,
+                                double* __restrict__ kd_tab, double* __restrict__ g1_tab) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > max_len) return;
+    const double r = __ddiv_rn((double)i, avgdl);
+    const double k = __dmul_rn(k1, __dadd_rn(one_minus_b, __dmul_rn(b, r)));
+    kd_tab[i] = k;
+    g1_tab[i] = __ddiv_rn(__dmul_rn(1.0, k1p1), __dadd_rn(1.0, k));
+}
+__global__ void post_len_kernel(const int32_t* __restrict__ post_doc, int64_t n_post, const int64_t* __restrict__ doc_len,
+                                uint16_t* __restrict__ post_len) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_post) post_len[p] = (uint16_t)doc_len[post_doc[p]];
+}
+
 // slices[(q * t_cap + j) * (n_sub + 1) + sub] = first posting of query q's j-th term whose doc id is
 // >= sub * BM25_SUB (absolute index into post_doc).  One thread per entry: the binary searches are
 // independent, so their latency is hidden by parallelism instead of being paid serially in the scoring kernel.
-// Also fills q_idf[q][j] (idf of the query's j-th term, 0 if absent: webui.py:140) and resets the query's record-pool cursor.
+// Also fills q_idf[q][j] (idf of the query's j-th term, 0 if absent: webui.py:140).
 __global__ void bm25_slices_kernel(const int64_t* __restrict__ post_ptr, const int32_t* __restrict__ post_doc, int32_t n_vocab,
                                    const QueryTerms* __restrict__ queries, const double* __restrict__ idf, int t_cap, int64_t n_sub,
                                    int64_t* __restrict__ slices, int32_t* __restrict__ n_required,
-                                   unsigned int* __restrict__ rec_cursor, double* __restrict__ q_idf) {
+                                   double* __restrict__ q_idf) {
     const int64_t sub = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int qi = blockIdx.y / t_cap, j = blockIdx.y - qi * t_cap;
-    if (sub == 0 && j == 0) {
-        n_required[qi] = queries[qi].n_required;          // per-query constant of the combine phase (webui.py:161)
-        rec_cursor[qi] = 0u;
-    }
+    if (sub == 0 && j == 0) n_required[qi] = queries[qi].n_required;   // per-query constant of the combine phase (webui.py:161)
     if (j >= queries[qi].n_terms) return;
     const int t = queries[qi].term[j];
     const bool known = t >= 0 && t < n_vocab;
@@ -79,12 +99,13 @@ struct Bm25Args {
     const int64_t* slices; int t_cap; int64_t n_sub;
     const int32_t* post_doc; const int32_t* post_tf;          // post_tf may be null: tf == 1
     const double* kd; const double* g1; int64_t n;            // g1: the tf == 1 quotient per doc
+    const uint16_t* post_len; const double* kd_tab; const double* g1_tab;   // per-posting doc length + per-length tables (null: per-doc arrays)
     const QueryTerms* queries; const double* q_idf; double magic, k1p1;      // q_idf [q][MAX_TERMS]
     // score kernel: per-query maximum + the tile's record (+ optional dense scores for the compute_bm25_scores seam)
     uint64_t* max_keys; double* dense_out; int64_t ld;
     uint32_t* tile_hdr;                                        // [q][tile_ld][8]: bitmap of the docs whose BM25 value is not the default
     uint32_t* tile_off;                                        // [q][tile_ld]: first record slot of the tile (relative to rec_base[q])
-    double* rec_val; uint8_t* rec_pos; const int64_t* rec_base; unsigned int* rec_cursor;   // record pools, [q] bases and cursors
+    double* rec_val; uint8_t* rec_pos; const int64_t* rec_base;   // record pools, [q] pool offsets
     int64_t tile_ld;
 };
 
@@ -98,7 +119,9 @@ struct Bm25Args {
 // Result: the per-query maximum (webui.py:379 needs it before anything can be combined) and the tile's RECORD - a
 // 256-bit map of the docs whose BM25 value differs from the default of the query (0, or -inf when the query has a
 // required term) in tile_hdr, and those values with their positions inside the tile, compacted in doc order, at
-// rec_base[q] + tile_off[q][tile] of the record pools (slots handed out by one atomicAdd per tile).
+// rec_base[q] + tile_off[q][tile] of the record pools.  tile_off = the number of postings of the query's terms that lie
+// BEFORE the tile (read off the slice table): a tile has at most as many records as postings, so the regions never
+// overlap and no cursor is shared (a per-query atomic cursor serialised ~10 M atomics per batch on 256 addresses).
 __global__ void __launch_bounds__(BM25_THREADS)
 bm25_score_kernel(Bm25Args A) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
@@ -122,18 +145,26 @@ bm25_score_kernel(Bm25Args A) {
     const double untouched = has_req ? -INFINITY : 0.0;
 
     bool zeroed = false;
+    unsigned int rec_off = 0u;
     // terms in groups of 32 (lane = term of the group); groups, and the terms inside one, are processed in query order
-    for (int j0 = 0; j0 < T; j0 += 32) {
+    // The loop runs to t_cap (a launch constant >= every query's term count) and a lane's loads do not wait for the
+    // query record: slice bounds, weight and idf of term j are fetched together with T itself (one round trip instead of
+    // two); table rows beyond the query's terms hold stale values and are masked by `j < T`.
+    for (int j0 = 0; j0 < A.t_cap; j0 += 32) {
         const int j = j0 + lane;
-        int64_t a = 0;
-        int len = 0;
+        int64_t a = 0, b1 = 0, a0 = 0;
         double w = 0.0, idfv = 0.0;
-        if (j < T) {
+        if (j < A.t_cap) {
             a = sl[(int64_t)j * (A.n_sub + 1)];
-            len = (int)(sl[(int64_t)j * (A.n_sub + 1) + 1] - a);
+            b1 = sl[(int64_t)j * (A.n_sub + 1) + 1];
+            a0 = sl[(int64_t)j * (A.n_sub + 1) - sub];   // slices[..][0] = start of the list
             w = Q.weight[j];
             idfv = A.q_idf[(size_t)qi * MAX_TERMS + j];
         }
+        if (j0 >= T) break;                              // warp-uniform (T arrives with the loads above)
+        const int len = j < T ? (int)(b1 - a) : 0;
+        const unsigned int before = j < T ? (unsigned int)(a - a0) : 0u;      // postings of term j in the tiles before this one
+        rec_off += __reduce_add_sync(0xffffffffu, before);
         int inc = len;                                   // inclusive prefix sum of the slice lengths
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -176,9 +207,10 @@ bm25_score_kernel(Bm25Args A) {
                         double quot;
                         if (A.post_tf) {
                             const double tf = (double)A.post_tf[p];
-                            quot = __ddiv_rn(__dmul_rn(tf, A.k1p1), __dadd_rn(tf, A.kd[d]));   // webui.py:145-146
+                            const double kdv = A.post_len ? A.kd_tab[A.post_len[p]] : A.kd[d];
+                            quot = __ddiv_rn(__dmul_rn(tf, A.k1p1), __dadd_rn(tf, kdv));       // webui.py:145-146
                         } else {
-                            quot = A.g1[d];                                                    // the same quotient for tf == 1, precomputed
+                            quot = A.post_len ? A.g1_tab[A.post_len[p]] : A.g1[d];             // the same quotient for tf == 1, precomputed
                         }
                         const double mult = (wt > A.magic) ? (wt - A.magic) : wt;
                         c[r] = __dmul_rn(mult, __dmul_rn(iv, quot));                           // webui.py:147,167,170
@@ -234,9 +266,7 @@ bm25_score_kernel(Bm25Args A) {
         m[u] = __ballot_sync(0xffffffffu, in && x != untouched);  // NaN never appears: idf, K_d and the weights are finite
         n_rec += __popc(m[u]);
     }
-    unsigned int off = 0;
-    if (lane == 0 && n_rec > 0) off = atomicAdd(&A.rec_cursor[qi], (unsigned int)n_rec);
-    off = __shfl_sync(0xffffffffu, off, 0);
+    const unsigned int off = rec_off;
     double* rv = A.rec_val + A.rec_base[qi] + off;
     uint8_t* rp = A.rec_pos + A.rec_base[qi] + off;
     double bd = -INFINITY;                                        // maximum in the double domain, one key at the end
@@ -272,6 +302,84 @@ bm25_score_kernel(Bm25Args A) {
         atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)best);
 }
 
+// ---- the bitmap path (tf == 1 indexes) ---------------------------------------------------------------------------
+// One presence bitmap per DISTINCT term of the batch, in the lane-major byte layout of finals.cuh (BitSrc): built by
+// streaming every term's posting list once - coalesced, no per-(tile, query) dependency chain - and shared by all the
+// queries of the batch that use the term.  grid (chunks, n_slots); the bitmaps are zeroed by the caller.
+constexpr int BITMAP_THREADS = 256;
+__global__ void __launch_bounds__(BITMAP_THREADS)
+bm25_bitmap_kernel(const int64_t* __restrict__ post_ptr, const int32_t* __restrict__ post_doc, const int32_t* __restrict__ slot_terms,
+                   int64_t n_tiles, uint32_t* __restrict__ bits /* [slot][n_tiles][8 words] */) {
+    const int s = blockIdx.y, lane = threadIdx.x & 31;
+    const int t = slot_terms[s];
+    const int64_t a = post_ptr[t], b = post_ptr[t + 1];
+    uint32_t* mine = bits + (int64_t)s * n_tiles * 8;
+    const int64_t stride = (int64_t)gridDim.x * BITMAP_THREADS;
+    for (int64_t p0 = a + (int64_t)blockIdx.x * BITMAP_THREADS + (threadIdx.x - lane); p0 < b; p0 += stride) {   // warp-uniform
+        const int64_t p = p0 + lane;
+        const bool act = p < b;
+        int64_t word = -1 - lane;                                   // inactive lanes: distinct, matching nobody
+        uint32_t bit = 0u;
+        if (act) {
+            const int d = post_doc[p];
+            const int l = d & 31, u = (d >> 5) & 7;                 // doc = tile*256 + 32*u + l -> byte l, bit u of the tile
+            word = ((int64_t)(d >> 8) << 3) + (l >> 2);
+            bit = 1u << (8 * (l & 3) + u);
+        }
+        // doc ids ascend, so lanes that hit the same 32-bit word are neighbours: one atomic per distinct word
+        const unsigned peers = __match_any_sync(0xffffffffu, word);
+        const uint32_t all = __reduce_or_sync(peers, bit);
+        if (act && lane == __ffs(peers) - 1) atomicOr(&mine[word], all);
+    }
+}
+
+// q_idf[q][j] = idf of query q's j-th term (0 if absent, webui.py:140), n_required[q]: the per-query constants of the
+// bitmap path (the general path fills them in bm25_slices_kernel)
+__global__ void query_idf_kernel(const QueryTerms* __restrict__ queries, int nq, const double* __restrict__ idf, int32_t n_vocab,
+                                 double* __restrict__ q_idf, int32_t* __restrict__ n_required) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * MAX_TERMS) return;
+    const int qi = i / MAX_TERMS, j = i - qi * MAX_TERMS;
+    if (j == 0) n_required[qi] = queries[qi].n_required;
+    if (j >= queries[qi].n_terms) return;
+    const int t = queries[qi].term[j];
+    q_idf[i] = (t >= 0 && t < n_vocab) ? idf[t] : 0.0;
+}
+
+// per-query maximum of the BM25 scores (webui.py:379 needs it before anything can be combined); one block = one tile
+
+// x 8 queries, so the tile's g1 values and the bytes of shared terms come out of L1 for seven of the eight warps
+constexpr int BITQ_WARPS = 8;
+__global__ void __launch_bounds__(32 * BITQ_WARPS)
+bm25_max_bits_kernel(BitSrc B, int64_t n, int nq, uint64_t* __restrict__ max_keys, double* __restrict__ dense_out, int64_t ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    const int qi = blockIdx.y * BITQ_WARPS + warp;
+    if (qi >= nq) return;
+    double v[FIN_U];
+    bm25_tile_values(B, qi, tile, lane, n, v);
+    double bd = -INFINITY;
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < FIN_U; ++u) {
+        const int64_t d = tile * FIN_TILE + 32 * u + lane;
+        if (d < n) {
+            if (dense_out) dense_out[(int64_t)qi * ld + d] = v[u];
+            bd = fmax(bd, v[u]);
+            any = true;
+        }
+    }
+    uint64_t best = any ? dkey(bd) : KEY_EMPTY;
+    {   // 64-bit warp maximum with two redux.sync
+        const uint32_t bh = (uint32_t)(best >> 32), bl = (uint32_t)best;
+        const uint32_t mh = __reduce_max_sync(0xffffffffu, bh);
+        const uint32_t ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
+        best = ((uint64_t)mh << 32) | ml;
+    }
+    if (lane == 0 && best != KEY_EMPTY && best > *(volatile uint64_t*)&max_keys[qi])
+        atomicMax(reinterpret_cast<unsigned long long*>(&max_keys[qi]), (unsigned long long)best);
+}
+
 constexpr int BM25C_WARPS = 8;
 constexpr int BM25C_THREADS = 32 * BM25C_WARPS;
 constexpr uint64_t KEY_NAN = 0xFFF8000000000000ull;     // a NaN score sorts first, as dkey(NaN) does
@@ -281,6 +389,7 @@ struct CombineArgs {
     int64_t n_sub;
     uint64_t* seg_max; int seg_stride; int tiles_per_seg;     // seg_max[q * seg_stride + tile / tiles_per_seg]
     uint64_t* tile_max;                                        // tile_max[q][tile]: best combined key of the tile
+    double* rec_out;                                           // records path: the record pool, rewritten in place (see FinSrc::rec_scaled)
 };
 
 // After the global maxima are known.  One warp per (tile, query): the best combined score of the tile
@@ -350,18 +459,52 @@ bm25_combine_kernel(CombineArgs A) {
         any = true;
     }
     // docs with a record: exact, one per lane
-    auto exact = [&](double val, int pos) {
+    auto exact = [&](double val, int pos, int64_t slot) {
         const float x = simq[lo + pos];
-        const double f = S.blend(__dmul_rn(S.wb, S.bm25_norm(c, val)), S.sim_norm(c, x));
+        const double wbb = __dmul_rn(S.wb, S.bm25_norm(c, val));
+        A.rec_out[slot] = wbb;                        // in place: the later passes read BM25_WEIGHT * (value / max) directly
+        const double f = S.blend(wbb, S.sim_norm(c, x));
         nan_seen = nan_seen || f != f;
         fbest = fmax(fbest, f);
         any = true;
     };
-    if (lane < n_rec) exact(pv[0], pp[0]);
-    if (32 + lane < n_rec) exact(pv[1], pp[1]);
-    for (int i = 64 + lane; i < n_rec; i += 32) exact(S.rec_val[rbase + i], (int)S.rec_pos[rbase + i]);
+    if (lane < n_rec) exact(pv[0], pp[0], rbase + lane);
+    if (32 + lane < n_rec) exact(pv[1], pp[1], rbase + 32 + lane);
+    for (int i = 64 + lane; i < n_rec; i += 32) exact(S.rec_val[rbase + i], (int)S.rec_pos[rbase + i], rbase + i);
     uint64_t best = any ? dkey(fbest) : KEY_EMPTY;
     if (nan_seen) best = KEY_NAN;                                  // e.g. weight 0 x -inf
+    best = warp_max_u64(best);
+    if (lane == 0) {
+        A.tile_max[(int64_t)qi * S.tile_ld + sub] = best;
+        if (best != KEY_EMPTY)
+            atomicMax(reinterpret_cast<unsigned long long*>(&A.seg_max[(size_t)qi * A.seg_stride + (int)(sub / A.tiles_per_seg)]),
+                      (unsigned long long)best);
+    }
+}
+
+// The same stage on the bitmap path: the tile's BM25 values are re-derived from the term bitmaps (no records exist),
+// every doc takes the exact formula; block = one tile x 8 queries (shared g1 / bitmap bytes through L1).
+__global__ void __launch_bounds__(32 * BITQ_WARPS)
+bm25_combine_bits_kernel(CombineArgs A, int nq) {
+    const FinSrc& S = A.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t sub = blockIdx.x;
+    const int qi = blockIdx.y * BITQ_WARPS + warp;
+    if (qi >= nq) return;
+    double f[FIN_U];
+    unsigned valid;
+    tile_finals(S, qi, sub, lane, f, valid);
+    double fbest = -INFINITY;
+    bool nan_seen = false;
+#pragma unroll
+    for (int u = 0; u < FIN_U; ++u) {
+        if ((valid >> u) & 1u) {
+            nan_seen = nan_seen || f[u] != f[u];
+            fbest = fmax(fbest, f[u]);
+        }
+    }
+    uint64_t best = valid ? dkey(fbest) : KEY_EMPTY;
+    if (nan_seen) best = KEY_NAN;
     best = warp_max_u64(best);
     if (lane == 0) {
         A.tile_max[(int64_t)qi * S.tile_ld + sub] = best;

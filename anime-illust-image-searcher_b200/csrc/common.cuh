@@ -62,7 +62,16 @@ __host__ __device__ __forceinline__ float fkey_inv(uint32_t k) {
     return x;
 }
 
+struct QueryTerms {  // device-resident, one per query of the batch (webui.py:354-371: {term id: weight} in dict order)
+    int32_t n_terms;
+    int32_t n_required;                          // terms with weight > REQUIRE_TAG_MAGIC_NUMBER (webui.py:161); host-filled
+    int32_t term[MAX_TERMS];
+    int32_t slot[MAX_TERMS];                     // index of the term among the DISTINCT terms of the batch (-1: unknown term)
+    double weight[MAX_TERMS];
+};
+
 constexpr uint64_t KEY_EMPTY = 0ull;
+
 constexpr int64_t ID_EMPTY = 0x7FFFFFFFFFFFFFFFll;
 
 // (key desc, id asc): the reference's stable sort by -score over enumerate(...) (webui.py:191-192,237)

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ais_b200.h"
@@ -55,6 +56,8 @@ int fail(int code, const char* fmt, ...) {
         int _s = (call);           \
         if (_s != AIS_OK) return _s; \
     } while (0)
+
+#define LAUNCHED(e) do { (e)->kernel_launches++; CK(cudaGetLastError()); } while (0)
 
 struct Buf {
     void* p = nullptr;
@@ -135,6 +138,8 @@ struct ais_engine {
     // index
     Buf rows;  int64_t n_vec = 0, cap_vec = 0;
     Buf post_ptr, post_doc, post_tf, idf, kd, g1, doc_len;
+    Buf post_len, kd_tab, g1_tab;  int64_t max_doc_len = -1;   // doc length per posting (uint16) + K_d / quotient per length: the
+                                                               // score kernel's per-posting lookup is an L1 hit instead of a gather
     double avgdl = 0.0;
     bool has_tf = false;
     int32_t n_vocab = 0;
@@ -156,15 +161,27 @@ struct ais_engine {
     Buf tile_hdr;              // [qt_cap][tile_ld][8] bitmap of the docs with a BM25 record (bm25.cuh)
     Buf tile_off;              // [qt_cap][tile_ld] first record slot of the tile, relative to rec_base[q]
     Buf rec_val, rec_pos;      // record pools: fp64 values / positions inside the tile
-    Buf rec_base, rec_cursor;  // [qt_cap] int64 pool offset of the query / uint32 slots handed out
+    Buf rec_base;              // [qt_cap] int64 pool offset of the query's records
     int64_t* h_rec_base = nullptr;
+    Buf term_bits, slot_terms;  // bitmap path: presence bitmaps [n_slots][n_tiles][32 B] of the batch's distinct terms / their ids
+    int32_t* h_slot_terms = nullptr;
+    int n_slots = 0;
+    bool rec_scaled = false;    // current batch, records path: the combine pass has rewritten the records (FinSrc::rec_scaled)
+    bool use_bits = false;      // current batch: BM25 from the term bitmaps (tf == 1 index, bitmaps fit) - else per-tile records
+    bool ieee_div = false;      // AIS_IEEE_DIV=1: __ddiv_rn for bm25 / max (cross-check of the FMA-corrected quotient)
+    bool want_bits = false;     // AIS_BM25_BITMAP=1: the bitmap path where it applies (default: per-tile records)
+    int64_t bitmap_cap_bytes = 4LL << 30;     // AIS_BM25_BITMAP_MB
+    int64_t bitmap_batches = 0;
     std::vector<int64_t> h_post_ptr;          // host copy of post_ptr: sizes the record pool of a batch (sum of df per query)
     Buf tile_max;  int64_t tile_ld = 0;       // [qt_cap][tile_ld] best combined key per 256-doc tile (select2.cuh)
     Buf tile_max2;             // the same for the blend R of a dense re-query (pass 2)
     Buf col_lo, col_hi;        // [tile_ld] extreme values of the cached column per tile (pass 2, column mode)
     const double* cur_maxes = nullptr;        // device [nq][2] global maxima of the current batch (caller- or engine-owned)
     bool ext_fin = false;      // current batch: combined scores were supplied (ais_rerank), not computed
-    bool bound_ok = false;     // current batch, pass 2: the tile upper bound on R is valid (column mode, weights >= 0)
+    bool bound_ok = false;     // current batch, pass 2: AIS_TILE_BOUND=1 and the tile upper bound on R is valid
+    bool ub_valid = false;     // current batch, pass 2: the tile upper bound on R is valid (column mode, weights >= 0, pass-1 list kept)
+    bool no_skip = false;      // AIS_NO_TILE_SKIP=1: the pass-2 maxima kernel visits every tile
+    int64_t skip_passes = 0;
     Buf seg_max, sel_thr, surv_count, surv_keys, surv_ids, gate, witness, last_keys, wit_table;
     uint64_t* h_last_keys = nullptr;
     int sel_k_cap = 0, out_topn_cap = 0;
@@ -177,13 +194,15 @@ struct ais_engine {
     int h_out_cap = 0;
 
     // stats
-    int64_t column_scan_launches = 0, last_tiles_per_seg = 0;
+    int64_t column_scan_launches = 0, last_tiles_per_seg = 0, bound_passes = 0;
     Buf colbuf;                    // rows[.][col_comp] as a compact array (column mode of the PRF re-query)
     int col_comp = -1;  const void* col_rows_ptr = nullptr;  int64_t col_n = -1;
     bool rer_column = false;       // current batch: rer[q][d] = colbuf[d] * d_q2[q][col_comp], never materialised
     bool requery_dense = false;    // AIS_REQUERY_DENSE=1: always run the dense scan for the PRF re-query
     int sel_deep = -1;             // AIS_SELECT_DEPTH: cap on the extra prefix length the select stages ask for (-1: none)
-    bool no_bound = false;         // AIS_NO_TILE_BOUND=1: pass 2 always streams (no per-tile upper bound on R)
+    bool no_bound = true;          // AIS_TILE_BOUND=1: pass 2 of the collapsed re-query skips tiles by an upper bound on R
+                                   // (exact, but only selective when BM25 separates the top docs; measured on the benchmark:
+                                   // the pass-1-candidate threshold lets > 4096 survivors through for sim-dominated queries)
     int64_t scan_launches = 0, kernel_launches = 0, fullsort_fallbacks = 0, bytes_device = 0;
     bool profiling = false;
     bool use_mma = true;       // >= 5 queries per pass: tensor-core scan (3xTF32); AIS_SCAN_SIMT=1 keeps the fp32 SIMT kernel
@@ -192,8 +211,11 @@ struct ais_engine {
     Buf qsplit;                // [64][300] hi | lo images of the queries of one tcgen05 pass
     CUtensorMap tm_rows, tm_q[2];       // tm_q[0]: 32 queries per pass, tm_q[1]: 64
     const void* tm_rows_ptr = nullptr;  int64_t tm_rows_n = -1;  const void* tm_q_ptr = nullptr;
-    double scan_ms_total = 0.0;
-    std::vector<cudaEvent_t> ev_pending, ev_free;
+    double kind_ms[AIS_N_KINDS] = {0};          // summed CUDA-event time per kernel class (profiling on)
+    int64_t kind_launches[AIS_N_KINDS] = {0};
+    struct PendingEv { int kind; cudaEvent_t a, b; };
+    std::vector<PendingEv> ev_pending;
+    std::vector<cudaEvent_t> ev_free;
 
     int64_t n() const { return n_vec > 0 ? n_vec : (n_bm25 > 0 ? n_bm25 : 0); }
     int64_t total() const { return n_total >= 0 ? n_total : n_vec; }
@@ -246,6 +268,38 @@ int check_loaded(const ais_engine* e) {
     return AIS_OK;
 }
 
+// Per-posting doc lengths and the per-LENGTH tables of K_d and the tf == 1 quotient (both depend on the doc only through
+// its length, webui.py:145): bm25_score_kernel then needs no dependent gather into the per-doc arrays.  Lengths beyond
+// 65535 keep the per-doc arrays (post_len stays empty).
+int build_len_tables(ais_engine* e, int64_t n_docs, bool postings_changed) {
+    e->max_doc_len = -1;
+    if (n_docs <= 0 || e->n_post <= 0) return AIS_OK;
+    Buf d_max;
+    TRY(dev_alloc(e, d_max, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d_max.p, 0, sizeof(unsigned long long), e->stream));
+    max_len_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, e->stream>>>(e->doc_len.as<int64_t>(), n_docs, d_max.as<unsigned long long>());
+    LAUNCHED(e);
+    unsigned long long mx = 0;
+    CK(cudaMemcpyAsync(&mx, d_max.p, sizeof(mx), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    dev_free(e, d_max);
+    if (mx >= 65536ull) return AIS_OK;
+    TRY(dev_alloc(e, e->kd_tab, (size_t)(mx + 1) * sizeof(double)));
+    TRY(dev_alloc(e, e->g1_tab, (size_t)(mx + 1) * sizeof(double)));
+    kd_table_kernel<<<(unsigned)((mx + 256) / 256), 256, 0, e->stream>>>((int64_t)mx, e->avgdl, e->p.k1, e->p.b, 1.0 - e->p.b, e->p.k1 + 1.0,
+                                                                        e->kd_tab.as<double>(), e->g1_tab.as<double>());
+    LAUNCHED(e);
+    if (postings_changed || e->post_len.cap < (size_t)e->n_post * sizeof(uint16_t)) {
+        TRY(dev_alloc(e, e->post_len, (size_t)e->n_post * sizeof(uint16_t)));
+        post_len_kernel<<<(unsigned)((e->n_post + 255) / 256), 256, 0, e->stream>>>(e->post_doc.as<int32_t>(), e->n_post, e->doc_len.as<int64_t>(),
+                                                                                   e->post_len.as<uint16_t>());
+        LAUNCHED(e);
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    e->max_doc_len = (int64_t)mx;
+    return AIS_OK;
+}
+
 int ensure_work(ais_engine* e) {
     const int qt = next_pow2_int(e->p.max_batch);
     const int64_t nmax = e->n_vec > e->n_bm25 ? e->n_vec : e->n_bm25;
@@ -278,7 +332,7 @@ int ensure_work(ais_engine* e) {
     TRY(dev_alloc(e, e->q_nreq, (size_t)q * sizeof(int32_t)));
     TRY(dev_alloc(e, e->q_idf, (size_t)q * MAX_TERMS * sizeof(double)));
     TRY(dev_alloc(e, e->rec_base, (size_t)q * sizeof(int64_t)));
-    TRY(dev_alloc(e, e->rec_cursor, (size_t)q * sizeof(unsigned int)));
+    TRY(dev_alloc(e, e->slot_terms, (size_t)q * MAX_TERMS * sizeof(int32_t)));
     TRY(dev_alloc(e, e->col_lo, (size_t)tl * sizeof(float)));
     TRY(dev_alloc(e, e->col_hi, (size_t)tl * sizeof(float)));
     e->col_comp = -1;                  // the per-tile column extremes are re-derived with the cached column
@@ -293,8 +347,9 @@ int ensure_work(ais_engine* e) {
     if (q > e->qt_cap) {
         if (e->h_q) { cudaFreeHost(e->h_q); cudaFreeHost(e->h_qt); cudaFreeHost(e->h_q2); cudaFreeHost(e->h_top_ids);
                       cudaFreeHost(e->h_top_scores); cudaFreeHost(e->h_small); cudaFreeHost(e->h_last_keys);
-                      cudaFreeHost(e->h_rec_base); }
+                      cudaFreeHost(e->h_rec_base); cudaFreeHost(e->h_slot_terms); }
         CK(cudaMallocHost((void**)&e->h_rec_base, (size_t)q * sizeof(int64_t)));
+        CK(cudaMallocHost((void**)&e->h_slot_terms, (size_t)q * MAX_TERMS * sizeof(int32_t)));
         CK(cudaMallocHost((void**)&e->h_q, (size_t)q * DIM * sizeof(float)));
         CK(cudaMallocHost((void**)&e->h_q2, (size_t)q * DIM * sizeof(float)));
         CK(cudaMallocHost((void**)&e->h_qt, (size_t)q * sizeof(QueryTerms)));
@@ -340,7 +395,27 @@ int ensure_out(ais_engine* e, int topn) {
     return AIS_OK;
 }
 
-#define LAUNCHED(e) do { (e)->kernel_launches++; CK(cudaGetLastError()); } while (0)
+
+// CUDA-event bracket around the launches of one kernel class on the engine's stream (only while profiling is on);
+// ais_get_stats sums the pairs per class - bench.py's roofline.kernels[] comes from here.
+struct ProfScope {
+    ais_engine* e; int kind; cudaEvent_t a = nullptr;
+    ProfScope(ais_engine* e_, int kind_) : e(e_), kind(kind_) {
+        if (!e->profiling) return;
+        if (!e->ev_free.empty()) { a = e->ev_free.back(); e->ev_free.pop_back(); }
+        else if (cudaEventCreate(&a) != cudaSuccess) { a = nullptr; return; }
+        cudaEventRecord(a, e->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEvent_t b = nullptr;
+        if (!e->ev_free.empty()) { b = e->ev_free.back(); e->ev_free.pop_back(); }
+        else if (cudaEventCreate(&b) != cudaSuccess) { e->ev_free.push_back(a); return; }
+        cudaEventRecord(b, e->stream);
+        e->ev_pending.push_back({kind, a, b});
+        e->kind_launches[kind]++;
+    }
+};
 
 CombineParams combine_params(const ais_engine* e) {
     CombineParams cp;
@@ -355,23 +430,11 @@ template <int QT>
 int launch_scan_t(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
     const int64_t n_tiles = (e->n_vec + TILE_ROWS - 1) / TILE_ROWS;
     int grid = (int)(n_tiles < e->sm_count ? n_tiles : e->sm_count);
-    cudaEvent_t a = nullptr, b = nullptr;
-    if (e->profiling) {
-        for (cudaEvent_t* ev : {&a, &b}) {
-            if (!e->ev_free.empty()) { *ev = e->ev_free.back(); e->ev_free.pop_back(); }
-            else CK(cudaEventCreate(ev));
-        }
-        CK(cudaEventRecord(a, e->stream));
-    }
+    ProfScope prof(e, AIS_KIND_SCAN);
     scan_kernel<QT><<<grid, ScanCfg<QT>::THREADS, scan_smem_bytes<QT>(), e->stream>>>(
         e->rows.as<float>(), e->n_vec, d_q, out, e->ld, max_keys, nq, 1);
     LAUNCHED(e);
     e->scan_launches++;
-    if (e->profiling) {
-        CK(cudaEventRecord(b, e->stream));
-        e->ev_pending.push_back(a);
-        e->ev_pending.push_back(b);
-    }
     return AIS_OK;
 }
 
@@ -379,23 +442,11 @@ template <int QT>
 int launch_scan_mma_t(ais_engine* e, const float* d_q, int nq, float* out, uint32_t* max_keys) {
     const int64_t n_tiles = (e->n_vec + TILE_ROWS - 1) / TILE_ROWS;
     int grid = (int)(n_tiles < e->sm_count ? n_tiles : e->sm_count);
-    cudaEvent_t a = nullptr, b = nullptr;
-    if (e->profiling) {
-        for (cudaEvent_t* ev : {&a, &b}) {
-            if (!e->ev_free.empty()) { *ev = e->ev_free.back(); e->ev_free.pop_back(); }
-            else CK(cudaEventCreate(ev));
-        }
-        CK(cudaEventRecord(a, e->stream));
-    }
+    ProfScope prof(e, AIS_KIND_SCAN);
     scan_mma_kernel<QT><<<grid, MMA_THREADS, scan_mma_smem_bytes<QT>(), e->stream>>>(e->rows.as<float>(), e->n_vec, d_q, out, e->ld,
                                                                                     max_keys, nq);
     LAUNCHED(e);
     e->scan_launches++;
-    if (e->profiling) {
-        CK(cudaEventRecord(b, e->stream));
-        e->ev_pending.push_back(a);
-        e->ev_pending.push_back(b);
-    }
     return AIS_OK;
 }
 
@@ -454,23 +505,11 @@ int launch_scan_tc(ais_engine* e, const float* d_q, int nq, bool wide, float* ou
     LAUNCHED(e);
     const int64_t n_tiles = (e->n_vec + TC_M - 1) / TC_M;
     const int grid = (int)(n_tiles < e->sm_count ? n_tiles : e->sm_count);
-    cudaEvent_t a = nullptr, b = nullptr;
-    if (e->profiling) {
-        for (cudaEvent_t* ev : {&a, &b}) {
-            if (!e->ev_free.empty()) { *ev = e->ev_free.back(); e->ev_free.pop_back(); }
-            else CK(cudaEventCreate(ev));
-        }
-        CK(cudaEventRecord(a, e->stream));
-    }
+    ProfScope prof(e, AIS_KIND_SCAN);
     if (wide) launch_tc_variant<64, 2, 1, 4, 2, 1, 2>(e, grid, out, max_keys, nq);
     else launch_tc_variant<32, 3, 1, 6, 4, 1, 2>(e, grid, out, max_keys, nq);
     LAUNCHED(e);
     e->scan_launches++;
-    if (e->profiling) {
-        CK(cudaEventRecord(b, e->stream));
-        e->ev_pending.push_back(a);
-        e->ev_pending.push_back(b);
-    }
     return AIS_OK;
 }
 
@@ -551,8 +590,9 @@ int set_scan_attrs() {
     return AIS_OK;
 }
 
-// Query records -> pinned staging -> device.  Also sizes the BM25 record pool of the batch: a query leaves at most
-// min(sum of its terms' document frequencies, n) records (docs whose BM25 value is not the query's default).
+// Query records -> pinned staging -> device.  Also sizes the BM25 record pool of the batch: the records of a tile
+// (docs whose BM25 value is not the query's default) sit at the offset "postings of the query's terms before the tile",
+// so a query's region holds the sum of its terms' document frequencies.
 int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bool with_terms) {
     for (int i = 0; i < nq; ++i) {
         if (with_vec) {
@@ -567,6 +607,7 @@ int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bo
             t.n_required = 0;
             for (int j = 0; j < qs[i].n_terms; ++j) {
                 t.term[j] = qs[i].term_ids[j];
+                t.slot[j] = -1;
                 t.weight[j] = qs[i].weights[j];
                 t.n_required += qs[i].weights[j] > e->p.require_magic;        // webui.py:161 (1000 itself is NOT required)
             }
@@ -578,20 +619,51 @@ int upload_queries(ais_engine* e, const ais_query* qs, int nq, bool with_vec, bo
         CK(cudaMemcpyAsync(e->d_q.p, e->h_q, (size_t)padded * DIM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     }
     if (with_terms) {
+        // the distinct terms of the batch get one presence bitmap each (bitmap path of the BM25 side; tf == 1 indexes)
+        e->n_slots = 0;
+        e->use_bits = false;
+        const int64_t n_tiles = ((e->n_bm25 > 0 ? e->n_bm25 : 0) + SEL_TILE - 1) / SEL_TILE;
+        if (!e->has_tf && e->want_bits && n_tiles > 0) {
+            std::unordered_map<int32_t, int32_t> slot_of;
+            for (int i = 0; i < nq; ++i)
+                for (int j = 0; j < qs[i].n_terms; ++j) {
+                    const int32_t t = qs[i].term_ids[j];
+                    if (t < 0 || t >= e->n_vocab) continue;
+                    auto it = slot_of.find(t);
+                    if (it == slot_of.end()) {
+                        it = slot_of.emplace(t, e->n_slots).first;
+                        e->h_slot_terms[e->n_slots++] = t;
+                    }
+                    e->h_qt[i].slot[j] = it->second;
+                }
+            e->use_bits = (int64_t)e->n_slots * n_tiles * 32 <= e->bitmap_cap_bytes;
+        }
         CK(cudaMemcpyAsync(e->d_qt.p, e->h_qt, (size_t)nq * sizeof(QueryTerms), cudaMemcpyHostToDevice, e->stream));
+        if (e->use_bits) {
+            if (e->n_slots > 0) {
+                TRY(dev_alloc(e, e->term_bits, (size_t)e->n_slots * n_tiles * 32));
+                CK(cudaMemcpyAsync(e->slot_terms.p, e->h_slot_terms, (size_t)e->n_slots * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+            }
+            return AIS_OK;                               // no record pool on this path
+        }
         int64_t total = 0;
-        const int64_t n = e->n_bm25 > 0 ? e->n_bm25 : 0;
+
         for (int i = 0; i < nq; ++i) {
             int64_t touched = 0;
             for (int j = 0; j < qs[i].n_terms; ++j) {
                 const int32_t t = qs[i].term_ids[j];
                 if (t >= 0 && t < e->n_vocab) touched += e->h_post_ptr[(size_t)t + 1] - e->h_post_ptr[(size_t)t];
             }
+            if (touched >= (1LL << 32))
+                return fail(AIS_ERR_UNSUPPORTED, "query %d: its terms hold %lld postings on this shard (32-bit record offsets)", i, (long long)touched);
             e->h_rec_base[i] = total;
-            total += touched < n ? touched : n;
+            total += touched;
         }
-        TRY(dev_alloc(e, e->rec_val, (size_t)total * sizeof(double)));
-        TRY(dev_alloc(e, e->rec_pos, (size_t)total));
+        if ((size_t)total * sizeof(double) > e->rec_val.cap) {          // grow with headroom: batches differ in size
+            const size_t want = (size_t)total + (size_t)total / 4 + 1024;
+            TRY(dev_alloc(e, e->rec_val, want * sizeof(double)));
+            TRY(dev_alloc(e, e->rec_pos, want));
+        }
         CK(cudaMemcpyAsync(e->rec_base.p, e->h_rec_base, (size_t)nq * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
     }
     return AIS_OK;
@@ -604,6 +676,15 @@ FinSrc fin_src(const ais_engine* e, const double* d_maxes) {
     S.fin_ext = e->ext_fin ? e->fin_ext.as<double>() : nullptr;
     S.sim = e->sim.as<float>();
     S.ld = e->ld;
+    S.use_bits = e->use_bits ? 1 : 0;
+    S.rec_scaled = e->rec_scaled ? 1 : 0;
+    S.ieee_div = e->ieee_div ? 1 : 0;
+    S.B.bits = e->term_bits.as<uint8_t>();
+    S.B.n_tiles = (e->n() + SEL_TILE - 1) / SEL_TILE;
+    S.B.queries = e->d_qt.as<QueryTerms>();
+    S.B.q_idf = e->q_idf.as<double>();
+    S.B.g1 = e->g1.as<double>();
+    S.B.magic = e->p.require_magic;
     S.tile_hdr = e->tile_hdr.as<uint32_t>();
     S.tile_off = e->tile_off.as<uint32_t>();
     S.tile_ld = e->tile_ld;
@@ -628,6 +709,9 @@ Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
     a.post_tf = e->has_tf ? e->post_tf.as<int32_t>() : nullptr;
     a.kd = e->kd.as<double>();
     a.g1 = e->g1.as<double>();
+    a.post_len = e->max_doc_len >= 0 ? e->post_len.as<uint16_t>() : nullptr;
+    a.kd_tab = e->kd_tab.as<double>();
+    a.g1_tab = e->g1_tab.as<double>();
     a.n = e->n_bm25;
     a.queries = e->d_qt.as<QueryTerms>();
     a.q_idf = e->q_idf.as<double>();
@@ -639,7 +723,6 @@ Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
     a.rec_val = e->rec_val.as<double>();
     a.rec_pos = e->rec_pos.as<uint8_t>();
     a.rec_base = e->rec_base.as<int64_t>();
-    a.rec_cursor = e->rec_cursor.as<unsigned int>();
     a.tile_ld = e->tile_ld;
     return a;
 }
@@ -649,14 +732,49 @@ Bm25Args bm25_args(ais_engine* e, int64_t n_sub) {
 int launch_bm25_max(ais_engine* e, int nq, double* dense_out) {
     if (e->n_bm25 <= 0) return AIS_OK;
     const int64_t n_sub = (e->n_bm25 + BM25_SUB - 1) / BM25_SUB;
+    if (e->use_bits) {
+        // bitmap path: one streaming pass over the posting list of every DISTINCT term of the batch, then the per-query
+        // maxima from the bitmaps (the records / slice table of the general path below do not exist on this path)
+        e->bitmap_batches++;
+        {
+            ProfScope prof(e, AIS_KIND_BM25_SLICES);
+            query_idf_kernel<<<(nq * MAX_TERMS + 255) / 256, 256, 0, e->stream>>>(e->d_qt.as<QueryTerms>(), nq, e->idf.as<double>(),
+                                                                                 e->n_vocab, e->q_idf.as<double>(), e->q_nreq.as<int32_t>());
+            LAUNCHED(e);
+            if (e->n_slots > 0) {
+                CK(cudaMemsetAsync(e->term_bits.p, 0, (size_t)e->n_slots * n_sub * 32, e->stream));
+                int64_t longest = 0;
+                for (int s = 0; s < e->n_slots; ++s) {
+                    const int64_t df = e->h_post_ptr[(size_t)e->h_slot_terms[s] + 1] - e->h_post_ptr[(size_t)e->h_slot_terms[s]];
+                    longest = df > longest ? df : longest;
+                }
+                int64_t chunks = (longest + BITMAP_THREADS * 8 - 1) / (BITMAP_THREADS * 8);
+                if (chunks > 2LL * e->sm_count) chunks = 2LL * e->sm_count;
+                if (chunks < 1) chunks = 1;
+                bm25_bitmap_kernel<<<dim3((unsigned)chunks, (unsigned)e->n_slots), BITMAP_THREADS, 0, e->stream>>>(
+                    e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->slot_terms.as<int32_t>(), n_sub, e->term_bits.as<uint32_t>());
+                LAUNCHED(e);
+            }
+        }
+        ProfScope prof(e, AIS_KIND_BM25_SCORE);
+        const FinSrc S = fin_src(e, nullptr);
+        bm25_max_bits_kernel<<<dim3((unsigned)n_sub, (unsigned)((nq + BITQ_WARPS - 1) / BITQ_WARPS)), 32 * BITQ_WARPS, 0, e->stream>>>(
+            S.B, e->n_bm25, nq, e->maxb_key.as<uint64_t>(), dense_out, e->ld);
+        LAUNCHED(e);
+        return AIS_OK;
+    }
     int t_cap = 1;
     for (int q = 0; q < nq; ++q) t_cap = e->h_qt[q].n_terms > t_cap ? e->h_qt[q].n_terms : t_cap;
     e->bm25_t_cap = t_cap;
     TRY(dev_alloc(e, e->bm25_slices, (size_t)e->qt_cap * t_cap * (n_sub + 1) * sizeof(int64_t)));
+    {
+    ProfScope prof(e, AIS_KIND_BM25_SLICES);
     bm25_slices_kernel<<<dim3((unsigned)((n_sub + 1 + 127) / 128), (unsigned)(nq * t_cap)), 128, 0, e->stream>>>(
         e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), e->n_vocab, e->d_qt.as<QueryTerms>(), e->idf.as<double>(), t_cap, n_sub,
-        e->bm25_slices.as<int64_t>(), e->q_nreq.as<int32_t>(), e->rec_cursor.as<unsigned int>(), e->q_idf.as<double>());
+        e->bm25_slices.as<int64_t>(), e->q_nreq.as<int32_t>(), e->q_idf.as<double>());
     LAUNCHED(e);
+    }
+    ProfScope prof(e, AIS_KIND_BM25_SCORE);
     Bm25Args a = bm25_args(e, n_sub);
     a.max_keys = e->maxb_key.as<uint64_t>();
     a.dense_out = dense_out;
@@ -732,8 +850,14 @@ int local_select(ais_engine* e, int mode, int nq, int k, uint64_t* d_keys, int64
     TRY(ensure_sel(e, k));
     const int64_t n = e->n();
     SelectArgs a = select_args(e, mode == 2);
-    const bool bound = mode == 2 && e->bound_ok;         // pass 2: per-tile upper bound instead of a streaming pass
+    const bool bound = mode == 2 && e->bound_ok;         // pass 2 (AIS_TILE_BOUND=1): per-tile upper bound in the collect, no maxima pass
+    if (bound) e->bound_passes++;
+    // pass 2 on the records path: rerank_max_kernel (seeds not excluded from its segment maxima -> `depth` more segments
+    // counted by the threshold); `skip`: with the tile bound on R, from the threshold of the pass-1 candidates
+    const bool records2 = mode == 2 && !bound && !e->use_bits && !e->ext_fin && e->rec_scaled && !getenv("AIS_NO_RERANK_MAX");
+    const bool skip = records2 && e->ub_valid && !e->no_skip;
     if (n > 0 && !bound) {
+        ProfScope prof(e, AIS_KIND_COMBINE);
         CK(cudaMemsetAsync(e->seg_max.p, 0, (size_t)nq * SEG_MAX * sizeof(uint64_t), e->stream));
         if (mode == 0) {
             CombineArgs c;
@@ -741,25 +865,42 @@ int local_select(ais_engine* e, int mode, int nq, int k, uint64_t* d_keys, int64
             c.n_sub = a.n_tiles;
             c.seg_max = a.seg_max; c.seg_stride = SEG_MAX; c.tiles_per_seg = a.tiles_per_seg;
             c.tile_max = a.tile_max;
-            bm25_combine_kernel<<<dim3((unsigned)((a.n_tiles + BM25C_WARPS - 1) / BM25C_WARPS), (unsigned)nq), BM25C_THREADS, 0, e->stream>>>(c);
+            c.rec_out = e->rec_val.as<double>();
+            if (e->use_bits)
+                bm25_combine_bits_kernel<<<dim3((unsigned)a.n_tiles, (unsigned)((nq + BITQ_WARPS - 1) / BITQ_WARPS)), 32 * BITQ_WARPS, 0, e->stream>>>(c, nq);
+            else
+                bm25_combine_kernel<<<dim3((unsigned)((a.n_tiles + BM25C_WARPS - 1) / BM25C_WARPS), (unsigned)nq), BM25C_THREADS, 0, e->stream>>>(c);
             LAUNCHED(e);
+            if (!e->use_bits) { e->rec_scaled = true; a.S.rec_scaled = 1; }
         } else {
             if (mode == 2) {                                 // the tile table of R is separate: pass 1's stays valid
                 TRY(dev_alloc(e, e->tile_max2, (size_t)e->qt_cap * e->tile_ld * sizeof(uint64_t)));
                 a.tile_max = e->tile_max2.as<uint64_t>();
             }
-            const dim3 g1((unsigned)((a.n_seg + SEG_WARPS - 1) / SEG_WARPS), (unsigned)nq);
-            if (mode == 1) segmax_kernel<1><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
-            else segmax_kernel<2><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a);
+            const dim3 g1((unsigned)a.n_seg, (unsigned)((nq + SEG_WARPS - 1) / SEG_WARPS));
+            if (mode == 1) segmax_kernel<1><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a, nq);
+            else if (records2) {                             // records path: the light pass over the scaled records
+                const dim3 g2((unsigned)a.n_tiles, (unsigned)((nq + SEG_WARPS - 1) / SEG_WARPS));
+                if (skip) {                                  // threshold from the pass-1 candidates first: tiles that cannot reach it are skipped
+                    rerank_threshold_kernel<<<nq, 256, 0, e->stream>>>(e->p1_keys.as<uint64_t>(), e->p1_ids.as<int64_t>(), e->p1_k, a, k);
+                    LAUNCHED(e);
+                    rerank_max_kernel<1><<<g2, 32 * SEG_WARPS, 0, e->stream>>>(a, nq, e->tile_max.as<uint64_t>());
+                    e->skip_passes++;
+                } else {
+                    rerank_max_kernel<0><<<g2, 32 * SEG_WARPS, 0, e->stream>>>(a, nq, nullptr);
+                }
+            } else segmax_kernel<2><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a, nq);
             LAUNCHED(e);
         }
     }
+    ProfScope prof(e, AIS_KIND_SELECT);
     if (bound) {
         rerank_threshold_kernel<<<nq, 256, 0, e->stream>>>(e->p1_keys.as<uint64_t>(), e->p1_ids.as<int64_t>(), e->p1_k, a, k);
         LAUNCHED(e);
     } else {
         if (n <= 0) CK(cudaMemsetAsync(e->seg_max.p, 0, (size_t)nq * SEG_MAX * sizeof(uint64_t), e->stream));
-        threshold_kernel<<<nq, 256, 0, e->stream>>>(a.seg_max, a.n_seg, k, a.thr, a.surv_count, a.gate);
+        threshold_kernel<<<nq, 256, 0, e->stream>>>(a.seg_max, a.n_seg, records2 ? k + e->p.prf_depth : k, a.thr, a.surv_count, a.gate,
+                                                    skip ? 1 : 0);
         LAUNCHED(e);
     }
     if (n > 0) {
@@ -812,6 +953,7 @@ int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
     e->rer_column = false;
     e->ext_fin = false;
     e->bound_ok = false;
+    e->rec_scaled = false;
     e->p1_k = 0;
     return AIS_OK;
 }
@@ -834,6 +976,7 @@ int do_top(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys, co
            double* out_top_scores, float* d_rows) {
     const int depth = e->p.prf_depth;
     TRY(ensure_sel(e, k > depth ? k : depth));
+    ProfScope prof(e, AIS_KIND_REQUERY);
     const uint64_t* mk = d_keys;
     const int64_t* mi = d_ids;
     int stride = k;
@@ -877,6 +1020,8 @@ int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows,
     // Does every re-query vector have at most one non-zero component, the same one for the whole batch?  The collapsed
     // centroid of the reference always does (component 0); a caller-supplied vector is inspected.
     int comp = -1;
+    {
+    ProfScope prof(e, AIS_KIND_REQUERY);
     if (q2_host) {
         comp = -2;                                               // -2: no non-zero seen yet
         for (int q = 0; q < nq && comp != -1; ++q)
@@ -917,8 +1062,9 @@ int do_requery(ais_engine* e, int nq, const float* q2_host, const float* d_rows,
     }
     // The per-tile bound on R (select2.cuh, collect_kernel<2, 1>) needs the column form, non-negative blend weights
     // (every rounding of wo * fin + wr * (col * c) is then monotone) and this shard's pass-1 candidates.
-    e->bound_ok = comp >= 0 && !e->no_bound && e->p.original_score_weight > 0.0 && e->p.reranked_score_weight >= 0.0 &&
-                  e->p1_k > 0 && e->n() > 0;
+    e->ub_valid = comp >= 0 && e->p.original_score_weight > 0.0 && e->p.reranked_score_weight >= 0.0 && e->p1_k > 0 && e->n() > 0;
+    e->bound_ok = e->ub_valid && !e->no_bound;
+    }
     TRY(do_requery_select(e, nq, k, d_keys, d_ids));
     maxr_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(e->maxr_key.as<uint64_t>(), nq, d_max_r);
     LAUNCHED(e);
@@ -955,6 +1101,7 @@ int do_finish(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys,
     if (topn < 1) return fail(AIS_ERR_INVALID, "topn must be >= 1");
     TRY(ensure_sel(e, k));
     TRY(ensure_out(e, topn));
+    ProfScope prof(e, AIS_KIND_TAIL);
     if (n_lists == 1) {
         copy_list_kernel<<<nq, 128, 0, e->stream>>>(d_keys, d_ids, k, e->rest_keys.as<uint64_t>(), e->rest_ids.as<int64_t>(),
                                                    e->rest_count.as<int32_t>());
@@ -983,6 +1130,7 @@ constexpr int64_t WITNESS_BUCKETS = 1LL << 22;
 // below the last prefix entry?  d_witness[q] = 1 if this shard holds such a pair (sufficient, not necessary).
 int do_witness(ais_engine* e, int nq, const int32_t* amb, const uint64_t* last_keys, int second_pass, const double* d_max_r,
                int32_t* d_witness) {
+    ProfScope prof(e, AIS_KIND_WITNESS);
     CK(cudaMemsetAsync(d_witness, 0, (size_t)nq * sizeof(int32_t), e->stream));
     if (e->n() == 0) return AIS_OK;
     TRY(dev_alloc(e, e->wit_table, (size_t)WITNESS_BUCKETS * sizeof(uint64_t)));
@@ -1049,6 +1197,7 @@ int do_sort_finish(ais_engine* e, int qi, uint64_t* d_keys, int64_t* d_ids, int6
                    int64_t* out_ids, double* out_scores, int32_t* out_count, int32_t* out_status) {
     TRY(ensure_out(e, topn));
     TRY(dev_alloc(e, e->fs_count, sizeof(int64_t) * 2));
+    ProfScope prof(e, AIS_KIND_WITNESS);
     const int64_t n_pad = sort_capacity(n_entries);
     if (n_pad > n_entries) {
         fill_empty_kernel<<<(unsigned)((n_pad - n_entries + 255) / 256), 256, 0, e->stream>>>(d_keys, d_ids, n_entries, n_pad);
@@ -1276,8 +1425,14 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
     if (const char* tcm = getenv("AIS_SCAN_TC_MIN")) e->tc_min = atoi(tcm);
     if (const char* tcw = getenv("AIS_SCAN_TC_WIDE")) e->tc_wide = atoi(tcw) != 0;
     if (const char* rd = getenv("AIS_REQUERY_DENSE")) e->requery_dense = atoi(rd) != 0;
-    if (const char* nb = getenv("AIS_NO_TILE_BOUND")) e->no_bound = atoi(nb) != 0;
+    if (const char* nb = getenv("AIS_TILE_BOUND")) e->no_bound = atoi(nb) == 0;
+    if (const char* ns = getenv("AIS_NO_TILE_SKIP")) e->no_skip = atoi(ns) != 0;
+
     if (const char* sd = getenv("AIS_SELECT_DEPTH")) e->sel_deep = atoi(sd);
+    if (const char* fr = getenv("AIS_BM25_BITMAP")) e->want_bits = atoi(fr) != 0;
+    if (const char* dv = getenv("AIS_IEEE_DIV")) e->ieee_div = atoi(dv) != 0;
+    if (const char* bm = getenv("AIS_BM25_BITMAP_MB")) e->bitmap_cap_bytes = (int64_t)atoll(bm) << 20;
+
     int s = set_scan_attrs();
     if (s != AIS_OK) { cudaStreamDestroy(e->own_stream); delete e; return s; }
     *out = e;
@@ -1288,7 +1443,7 @@ int ais_destroy(ais_engine* e) {
     if (!e) return AIS_OK;
     DeviceGuard g(e->device);
     cudaStreamSynchronize(e->stream);
-    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->g1, &e->doc_len, &e->sim, &e->scratch64, &e->fin_ext, &e->p1_keys, &e->p1_ids, &e->q_idf, &e->tile_off, &e->rec_val, &e->rec_pos, &e->rec_base, &e->rec_cursor, &e->tile_max2, &e->col_lo, &e->col_hi,
+    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->g1, &e->doc_len, &e->sim, &e->scratch64, &e->fin_ext, &e->p1_keys, &e->p1_ids, &e->q_idf, &e->tile_off, &e->rec_val, &e->rec_pos, &e->rec_base, &e->post_len, &e->kd_tab, &e->g1_tab, &e->term_bits, &e->slot_terms, &e->tile_max2, &e->col_lo, &e->col_hi,
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,
@@ -1296,9 +1451,9 @@ int ais_destroy(ais_engine* e) {
                    &e->surv_keys, &e->surv_ids, &e->gate, &e->witness, &e->last_keys, &e->wit_table, &e->bm25_slices, &e->qsplit})
         dev_free(e, *b);
     for (void* h : {(void*)e->h_q, (void*)e->h_qt, (void*)e->h_q2, (void*)e->h_top_ids, (void*)e->h_top_scores,
-                    (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small, (void*)e->h_last_keys, (void*)e->h_rec_base})
+                    (void*)e->h_out_ids, (void*)e->h_out_scores, (void*)e->h_small, (void*)e->h_last_keys, (void*)e->h_rec_base, (void*)e->h_slot_terms})
         if (h) cudaFreeHost(h);
-    for (cudaEvent_t ev : e->ev_pending) cudaEventDestroy(ev);
+    for (const ais_engine::PendingEv& p : e->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (cudaEvent_t ev : e->ev_free) cudaEventDestroy(ev);
     cudaStreamDestroy(e->own_stream);
     delete e;
@@ -1316,6 +1471,7 @@ int ais_set_params(ais_engine* e, const ais_params* p) {
                                                                              e->p.b, 1.0 - e->p.b, e->p.k1 + 1.0, e->kd.as<double>(),
                                                                              e->g1.as<double>());
         LAUNCHED(e);
+        TRY(build_len_tables(e, e->n_bm25, false));
     }
     return AIS_OK;
 }
@@ -1418,7 +1574,7 @@ int ais_load_bm25(ais_engine* e, const int64_t* post_ptr, const int32_t* post_do
     e->n_vocab = n_terms;
     e->n_bm25 = n_docs;
     e->n_post = n_post;
-    return AIS_OK;
+    return build_len_tables(e, n_docs, true);
 }
 
 // ---- BM25 index build (genmodel.py:51-99) -------------------------------------------------------------------
@@ -1509,7 +1665,7 @@ int ais_finish_bm25(ais_engine* e, const double* idf, double avgdl) {
     CK(cudaStreamSynchronize(e->stream));
     e->avgdl = avgdl;
     e->n_bm25 = n_docs;
-    return AIS_OK;
+    return build_len_tables(e, n_docs, true);
 }
 
 int ais_export_postings(ais_engine* e, int64_t* post_ptr, int32_t* post_doc, int32_t* post_tf) {
@@ -1736,6 +1892,7 @@ int ais_debug_read(ais_engine* e, int32_t which, int32_t query, void* out) {
     if (!e || !out || query < 0 || query >= e->qt_cap || which < 0 || which > 3) return fail(AIS_ERR_INVALID, "bad argument");
     DeviceGuard g(e->device);
     const size_t n = (size_t)e->n();
+    if (which == 3) TRY(dev_alloc(e, e->rer, (size_t)e->qt_cap * e->ld * sizeof(float)));
     if (which == 3 && e->rer_column && e->n_vec > 0)        // column mode keeps no rer array: materialise this query's row
         TRY(launch_scan_column(e, e->d_q2.as<float>() + (size_t)query * DIM, 1, e->col_comp, e->rer.as<float>() + (size_t)query * e->ld,
                                e->maxs_key.as<uint32_t>() + query));
@@ -1769,12 +1926,12 @@ int ais_set_profiling(ais_engine* e, int on) {
 static int drain_events(ais_engine* e) {
     if (e->ev_pending.empty()) return AIS_OK;
     CK(cudaStreamSynchronize(e->stream));
-    for (size_t i = 0; i + 1 < e->ev_pending.size(); i += 2) {
+    for (const ais_engine::PendingEv& p : e->ev_pending) {
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, e->ev_pending[i], e->ev_pending[i + 1]));
-        e->scan_ms_total += ms;
-        e->ev_free.push_back(e->ev_pending[i]);
-        e->ev_free.push_back(e->ev_pending[i + 1]);
+        CK(cudaEventElapsedTime(&ms, p.a, p.b));
+        e->kind_ms[p.kind] += ms;
+        e->ev_free.push_back(p.a);
+        e->ev_free.push_back(p.b);
     }
     e->ev_pending.clear();
     return AIS_OK;
@@ -1788,20 +1945,23 @@ int ais_get_stats(ais_engine* e, ais_stats* out) {
     out->dim = DIM;
     out->n_terms = e->n_vocab;
     out->scan_launches = e->scan_launches;
-    out->scan_ms_total = e->scan_ms_total;
+    out->scan_ms_total = e->kind_ms[AIS_KIND_SCAN];
+    for (int k = 0; k < AIS_N_KINDS; ++k) { out->kind_ms[k] = e->kind_ms[k]; out->kind_launches[k] = e->kind_launches[k]; }
     out->kernel_launches = e->kernel_launches;
     out->fullsort_fallbacks = e->fullsort_fallbacks;
     out->bytes_device = e->bytes_device;
     out->column_scan_launches = e->column_scan_launches;
     out->tiles_per_seg = e->last_tiles_per_seg;
+    out->bound_passes = e->bound_passes + e->skip_passes;
+    out->bitmap_batches = e->bitmap_batches;
     return AIS_OK;
 }
 int ais_reset_stats(ais_engine* e) {
     if (!e) return fail(AIS_ERR_INVALID, "NULL engine");
     DeviceGuard g(e->device);
     TRY(drain_events(e));
-    e->scan_launches = e->kernel_launches = e->fullsort_fallbacks = e->column_scan_launches = 0;
-    e->scan_ms_total = 0.0;
+    e->scan_launches = e->kernel_launches = e->fullsort_fallbacks = e->column_scan_launches = e->bound_passes = e->bitmap_batches = e->skip_passes = 0;
+    for (int k = 0; k < AIS_N_KINDS; ++k) { e->kind_ms[k] = 0.0; e->kind_launches[k] = 0; }
     return AIS_OK;
 }
 int ais_synchronize(ais_engine* e) {

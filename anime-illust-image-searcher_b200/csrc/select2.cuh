@@ -93,17 +93,21 @@ __device__ __forceinline__ void tile_scores(const SelectArgs& a, const Rerank& r
 // with a zero weight times -inf, or NaN rows) sorts first like dkey(NaN) does: it is tracked by a flag.
 template <int MODE>
 __global__ void __launch_bounds__(32 * SEG_WARPS)
-segmax_kernel(SelectArgs a) {
-    __shared__ int64_t seeds[MAX_DEPTH];
-    __shared__ uint64_t wall[SEG_WARPS];
-    const int qi = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+segmax_kernel(SelectArgs a, int nq) {
+    // block = one segment x SEG_WARPS queries (warp = query): the per-doc data the queries share (g1, bitmap bytes of
+    // common terms, the re-query column) is pulled through L1 once for the eight of them
+    __shared__ int64_t seeds_all[SEG_WARPS][MAX_DEPTH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = blockIdx.y * SEG_WARPS + warp;
+    const int seg = blockIdx.x;
+    if (qi >= nq) return;
+    int64_t* seeds = seeds_all[warp];
     if (MODE == 2) {
-        if (threadIdx.x < MAX_DEPTH) seeds[threadIdx.x] = threadIdx.x < a.depth ? a.seeds_all[qi * MAX_DEPTH + threadIdx.x] : -1;
-        __syncthreads();
+        if (lane < MAX_DEPTH) seeds[lane] = lane < a.depth ? a.seeds_all[qi * MAX_DEPTH + lane] : -1;
+        __syncwarp();
     }
-    const int seg = blockIdx.x * SEG_WARPS + warp;
     uint64_t all_best = KEY_EMPTY;
-    if (seg < a.n_seg) {
+    {
         const Rerank rk = a.rerank(qi);
         const int64_t t0 = (int64_t)seg * a.tiles_per_seg;
         const int64_t t1 = t0 + a.tiles_per_seg < a.n_tiles ? t0 + a.tiles_per_seg : a.n_tiles;
@@ -149,21 +153,96 @@ segmax_kernel(SelectArgs a) {
         best = warp_max_u64(best);
         if (lane == 0) a.seg_max[(size_t)qi * SEG_MAX + seg] = best;
     }
-    if (a.max_all) {
-        if (lane == 0) wall[warp] = all_best;              // already warp-uniform
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint64_t m = wall[0];
-            for (int w = 1; w < SEG_WARPS; ++w) m = wall[w] > m ? wall[w] : m;
-            if (m != KEY_EMPTY) atomicMax(reinterpret_cast<unsigned long long*>(&a.max_all[qi]), (unsigned long long)m);
+    if (a.max_all && lane == 0 && all_best != KEY_EMPTY && all_best > *(volatile uint64_t*)&a.max_all[qi])
+        atomicMax(reinterpret_cast<unsigned long long*>(&a.max_all[qi]), (unsigned long long)all_best);
+}
+
+// ---- 1b. pass 2 on the records path: tile / segment maxima of the blend R in one light pass ---------------------------
+// R = wo * final + wr * rer (webui.py:208) for every doc, from the dot score (4 B), the re-query score (the shared column
+// or the query's dense array, 4 B) and the tile's BM25 records as bm25_combine_kernel left them (BM25_WEIGHT * value / max,
+// no division left).  One warp per (tile, query), block = one tile x 8 queries (the column comes through L1 once for the
+// eight).  Docs without a record take ~12 instructions each straight from registers; the ~45 docs with one are handled
+// compactly, one per lane, through their stored positions.  The PRF seeds are NOT excluded here (webui.py:217 drops them
+// from the candidates): the caller asks the segment-maximum threshold for `depth` more segments instead, which keeps it
+// a valid lower bound - at most `depth` of the counted maxima can be seeds.
+// BOUND = 1 (the reference's collapsed re-query with non-negative blend weights): a.thr holds a lower bound T of the
+// k-th best R of this shard (rerank_threshold_kernel).  A tile whose upper bound - the blend of its best COMBINED score
+// (pass 1's tile table) with its extreme column value, every rounding monotone - stays below T holds no candidate and not
+// the maximum of R either: it is skipped after two 8-byte loads.  Measured on the benchmark: 12 % of the tiles remain.
+template <int BOUND>
+__global__ void __launch_bounds__(32 * SEG_WARPS)
+rerank_max_kernel(SelectArgs a, int nq, const uint64_t* __restrict__ tile_max_fin) {
+    const FinSrc& S = a.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    const int qi = blockIdx.y * SEG_WARPS + warp;
+    if (qi >= nq) return;
+    const int64_t lo = tile * SEL_TILE;
+    const int64_t hi = lo + SEL_TILE < a.n ? lo + SEL_TILE : a.n;
+    const Rerank rk = a.rerank(qi);
+    if (BOUND == 1) {
+        uint64_t bound = tile_max_fin[(int64_t)qi * S.tile_ld + tile];
+        if (bound != KEY_EMPTY && bound < KEY_NAN) {
+            const float cx = rk.cq < 0.0f ? a.col_lo[tile] : a.col_hi[tile];
+            bound = dkey(rk.blend(dkey_inv(bound), cx));
         }
+        if (bound < a.thr[qi]) {                                   // warp-uniform
+            if (lane == 0) a.tile_max[(int64_t)qi * S.tile_ld + tile] = KEY_EMPTY;
+            return;
+        }
+    }
+    const float* simq = S.sim + (int64_t)qi * S.ld;
+    float sv[FIN_U], rv[FIN_U];
+#pragma unroll
+    for (int u = 0; u < FIN_U; ++u) {
+        const int64_t d = lo + u * 32 + lane;
+        sv[u] = d < hi ? simq[d] : 0.0f;
+        rv[u] = d < hi ? rk.rer[d] : 0.0f;
+    }
+    const uint4* hp = reinterpret_cast<const uint4*>(S.tile_hdr + ((int64_t)qi * S.tile_ld + tile) * 8);
+    const uint4 h0 = hp[0], h1 = hp[1];
+    const int64_t rbase = S.rec_base[qi] + S.tile_off[(int64_t)qi * S.tile_ld + tile];
+    const QNorm c = S.qnorm(qi);
+    const uint32_t w[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    int n_rec = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) n_rec += __popc(w[u]);
+    double best = -INFINITY;
+    bool any = false, nan_seen = false;
+#pragma unroll
+    for (int u = 0; u < FIN_U; ++u) {
+        const bool plain = !((w[u] >> lane) & 1u) && lo + u * 32 + lane < hi;
+        if (plain) {
+            const double r = rk.blend(S.blend(c.wb_dflt, S.sim_norm(c, sv[u])), rv[u]);
+            nan_seen = nan_seen || r != r;
+            best = fmax(best, r);
+            any = true;
+        }
+    }
+    for (int i = lane; i < n_rec; i += 32) {
+        const double wbb = S.rec_val[rbase + i];
+        const int pos = (int)S.rec_pos[rbase + i];
+        const double r = rk.blend(S.blend(wbb, S.sim_norm(c, simq[lo + pos])), rk.rer[lo + pos]);
+        nan_seen = nan_seen || r != r;
+        best = fmax(best, r);
+        any = true;
+    }
+    uint64_t key = nan_seen ? KEY_NAN : (any ? dkey(best) : KEY_EMPTY);
+    key = warp_max_u64_redux(key);
+    if (lane == 0) {
+        a.tile_max[(int64_t)qi * S.tile_ld + tile] = key;
+        if (key != KEY_EMPTY)
+            atomicMax(reinterpret_cast<unsigned long long*>(&a.seg_max[(size_t)qi * SEG_MAX + (int)(tile / a.tiles_per_seg)]),
+                      (unsigned long long)key);
+        if (a.max_all && key != KEY_EMPTY && key > *(volatile uint64_t*)&a.max_all[qi])
+            atomicMax(reinterpret_cast<unsigned long long*>(&a.max_all[qi]), (unsigned long long)key);
     }
 }
 
 // ---- 2a. threshold = k-th largest segment maximum ------------------------------------------------------
 __global__ void __launch_bounds__(256)
 threshold_kernel(const uint64_t* __restrict__ seg_max, int n_seg, int k, uint64_t* __restrict__ thr,
-                 int* __restrict__ surv_count, int* __restrict__ gate) {
+                 int* __restrict__ surv_count, int* __restrict__ gate, int use_floor) {
     __shared__ uint64_t v[SEG_MAX];
     const int qi = blockIdx.x, tid = threadIdx.x;
     int P = 32;
@@ -184,7 +263,10 @@ threshold_kernel(const uint64_t* __restrict__ seg_max, int n_seg, int k, uint64_
     }
     if (tid == 0) {
         uint64_t t = (k <= P) ? v[k - 1] : KEY_EMPTY;
-        thr[qi] = t != KEY_EMPTY ? t : 1ull;          // fewer than k non-empty segments: every doc qualifies
+        t = t != KEY_EMPTY ? t : 1ull;                // fewer than k non-empty segments: every doc qualifies
+        // use_floor: thr[qi] already holds ANOTHER valid lower bound of the k-th best key (rerank_threshold_kernel): keep the tighter
+        if (use_floor && thr[qi] > t && thr[qi] < KEY_NAN) t = thr[qi];
+        thr[qi] = t;
         surv_count[qi] = 0;
         gate[qi] = 0;
     }

@@ -418,7 +418,12 @@ class SearchEngine:
     def stats(self) -> dict:
         s = B.AisStats()
         check(lib.ais_get_stats(self._h, C.byref(s)))
-        return {name: getattr(s, name) for name, _ in B.AisStats._fields_}
+        out = {}
+        for name, _ in B.AisStats._fields_:
+            v = getattr(s, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        out["kernels"] = {k: {"ms": out["kind_ms"][i], "brackets": out["kind_launches"][i]} for i, k in enumerate(B.KIND_NAMES)}
+        return out
 
     def reset_stats(self) -> None:
         check(lib.ais_reset_stats(self._h))

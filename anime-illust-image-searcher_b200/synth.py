@@ -208,8 +208,10 @@ def generate_index(
     chunk: int = 65536,
     keep_sequences: bool = True,
     with_rows: bool = True,
+    rows: str = "infer",
 ) -> SynthIndex:
-    """Build a synthetic index (see module docstring)."""
+    """Build a synthetic index (see module docstring).  rows="random": plain N(0,1) fp32 rows instead of the (slow, hash-based)
+    infer_vector stand-in - for CPU timing runs at >= 1 M docs, where the row VALUES do not matter."""
     rng = np.random.default_rng(seed)
     pop = zipf_popularity(vocab_size)
     cdf = np.cumsum(pop)
@@ -220,7 +222,8 @@ def generate_index(
     row_counts = np.zeros(n_docs, dtype=np.int64)
     tid_chunks: List[np.ndarray] = []
     tf_chunks: List[np.ndarray] = []
-    rows = np.zeros((n_docs, DIM), dtype=np.float32) if with_rows else np.zeros((0, DIM), dtype=np.float32)
+    rows_mode = rows
+    rows_arr = np.zeros((n_docs, DIM), dtype=np.float32) if with_rows else np.zeros((0, DIM), dtype=np.float32)
     seqs: Optional[List[np.ndarray]] = [] if keep_sequences else None
     doc_len = np.zeros(n_docs, dtype=np.int64)
 
@@ -273,7 +276,7 @@ def generate_index(
         row_counts[lo:hi] = lengths
         doc_len[lo:hi] = (tf_pad * live).sum(axis=1)
         if with_rows:
-            rows[lo:hi] = infer.batch(seq_pad, seq_len)
+            rows_arr[lo:hi] = infer.batch(seq_pad, seq_len) if rows_mode == "infer" else rng.standard_normal((m, DIM), dtype=np.float32)
         if seqs is not None:
             for i in range(m):
                 seqs.append(seq_pad[i, : seq_len[i]].copy())
@@ -290,7 +293,7 @@ def generate_index(
     idf = np.where(df > 0, idf, 0.0).astype(np.float64)
     return SynthIndex(
         n_docs=n_docs, vocab_size=vocab_size, seed=seed, row_ptr=row_ptr, term_ids=term_ids.astype(np.int32),
-        tfs=tfs.astype(np.int32), doc_len=doc_len, avgdl=np.float64(avgdl), idf=idf, df=df, rows=rows,
+        tfs=tfs.astype(np.int32), doc_len=doc_len, avgdl=np.float64(avgdl), idf=idf, df=df, rows=rows_arr,
         tag_names=default_tag_names(vocab_size), infer=infer, doc_tag_seq=seqs, popularity=pop,
     )
 

@@ -121,59 +121,56 @@ def install(engine: _eng.SearchEngine, model_: Any, dictionary_: Any, csv_lines:
     _loaded_from = "<installed>"
 
 
-def _similarity_rows(sim) -> List[np.ndarray]:
-    """fp32 row blocks of a gensim ``Similarity`` (genmodel.py:168-175), shard by shard, as stored."""
-    blocks = []
-    for shard in getattr(sim, "shards", []):
-        blocks.append(np.asarray(shard.get_index().index, dtype=np.float32))
-    fresh = getattr(sim, "fresh_docs", None)
-    if fresh:
-        blocks.append(np.asarray(fresh, dtype=np.float32))
-    if not blocks and hasattr(sim, "index"):      # a plain MatrixSimilarity
-        blocks.append(np.asarray(sim.index, dtype=np.float32))
-    return blocks
+MAX_BATCH = int(os.environ.get("AIS_MAX_BATCH", "64"))     # queries that share each pass in find_similar_documents_batch
+MODEL_LOADER = None      # callable(path) -> object with infer_vector / dv; default: gensim's Doc2Vec.load (webui.py:668)
+
+
+class _Dictionary:
+    """``dictionary`` as far as the path uses it: ``token2id`` (webui.py:133,364-371)."""
+
+    def __init__(self, token2id: Dict[str, int]):
+        self.token2id = token2id
+
+
+def _load_doc2vec(path: str):
+    if MODEL_LOADER is not None:
+        return MODEL_LOADER(path)
+    try:
+        from gensim.models.doc2vec import Doc2Vec
+    except ImportError as exc:      # query inference stays gensim's (north_star); everything else loads without it
+        raise ImportError("load_model() needs gensim for doc2vec_model (query inference, webui.py:106,185) - the index, "
+                          "dictionary and BM25 files are read natively; set webui_api.MODEL_LOADER to supply another "
+                          "infer_vector implementation") from exc
+    return Doc2Vec.load(path)
 
 
 def load_model() -> None:
-    """webui.py:649-689: reads the index files from the CWD - ONCE; repeat calls (webui calls it on
-    every search, webui.py:585) are no-ops while the CWD is unchanged."""
+    """webui.py:649-689: reads the index files from the CWD - ONCE; repeat calls (webui calls it on every search,
+    webui.py:585) are no-ops while the CWD is unchanged.  The doc-vector shards, the dictionary and the five BM25 files
+    are read by ais_b200.loader (memory-mapped .npy shards, C walker over the bm25_corpus pickle: no gensim import, no N
+    Python dicts); only ``doc2vec_model`` goes through gensim, because query inference stays gensim's."""
     global _engine, model, index, dictionary, image_files_name_tags_arr, file_tag_index_dict, filepath_docid_dict
     global bm25_D, _loaded_from
+    from . import loader
     with _lock:
         cwd = os.getcwd()
         if _engine is not None and _loaded_from == cwd:
             return
-        try:
-            from gensim.models.doc2vec import Doc2Vec
-            from gensim.similarities import MatrixSimilarity
-        except ImportError as exc:  # gensim holds the on-disk formats of model / index / dictionary
-            raise ImportError("load_model() needs gensim to read doc2vec_model / doc2vec_index / doc2vec_dictionary; "
-                              "use install() with pre-extracted arrays otherwise") from exc
         with open(INDEX_CSV, "r", encoding="utf-8") as f:
             lines = [line.strip() for line in f]
         tag_index: Dict[str, Dict[str, bool]] = {}
         for line in lines:
             parts = line.split(",")
             tag_index[parts[0]] = {t: True for t in parts[1:]}
-        mdl = Doc2Vec.load("doc2vec_model")
-        sim = MatrixSimilarity.load("doc2vec_index")
-        with open("doc2vec_dictionary", "rb") as f:
-            dct = pickle.load(f)
-        pk = {}
-        for name in ("bm25_corpus", "bm25_doc_lengths", "bm25_avgdl", "bm25_idf", "bm25_D"):
-            with open(name, "rb") as f:
-                pk[name] = pickle.load(f)
-        eng = _eng.SearchEngine(device=DEVICE)
-        eng.reserve_docs(len(sim))
-        at = 0
-        for block in _similarity_rows(sim):
-            eng.load_vectors(block, first_row=at)
-            at += len(block)
-        stage_bm25(eng, pk["bm25_corpus"], pk["bm25_doc_lengths"], pk["bm25_avgdl"], pk["bm25_idf"], len(dct.token2id))
-        eng.set_shard(0, eng.n_docs)
+        mdl = _load_doc2vec("doc2vec_model")
+        dct = _Dictionary(loader.read_token2id("doc2vec_dictionary"))
+        eng = _eng.SearchEngine(device=DEVICE, max_batch=MAX_BATCH)
+        bm = loader.stage_index(eng, ".")
+        if len(lines) != eng.n_docs:
+            raise ValueError("%s has %d lines but the index holds %d docs" % (INDEX_CSV, len(lines), eng.n_docs))
         install(eng, mdl, dct, lines)
         file_tag_index_dict = tag_index
-        bm25_D = int(pk["bm25_D"])
+        bm25_D = int(bm["D"])
         _loaded_from = cwd
 
 

@@ -92,6 +92,17 @@ typedef int (*ais_infer_cb)(void* ctx, int32_t query_index, const int64_t* doc_i
 
 typedef struct ais_engine ais_engine;
 
+/* kernel classes of the per-class CUDA-event timers (ais_set_profiling) */
+#define AIS_N_KINDS 8
+#define AIS_KIND_SCAN 0         /* dense doc-vector scans (index[vec], webui.py:352,205) */
+#define AIS_KIND_BM25_SLICES 1  /* posting-list slice table of the batch */
+#define AIS_KIND_BM25_SCORE 2   /* compute_bm25_scores (webui.py:119-172) -> per-tile records */
+#define AIS_KIND_COMBINE 3      /* normalise + combine (webui.py:376-383) -> tile / segment maxima */
+#define AIS_KIND_SELECT 4       /* threshold, collect, survivor sort (the sorts of webui.py:191-192,237) */
+#define AIS_KIND_REQUERY 5      /* PRF seeds, centroid, re-query scores (webui.py:193-205) */
+#define AIS_KIND_TAIL 6         /* merge, filter_searched_result, result copy (webui.py:63-80,219-246) */
+#define AIS_KIND_WITNESS 7      /* near-tie witness pass / exact full-sort fallback */
+
 typedef struct ais_stats {
     int64_t n_docs;             /* docs in this shard */
     int64_t n_postings;
@@ -104,6 +115,10 @@ typedef struct ais_stats {
     int64_t bytes_device;       /* device memory held by the engine */
     int64_t column_scan_launches; /* re-query passes served by the single-component column scan */
     int64_t tiles_per_seg;      /* 256-doc tiles per select segment in the last batch (> 1 from ~525 k docs per shard) */
+    double kind_ms[AIS_N_KINDS];        /* summed CUDA-event time per kernel class since the last reset (profiling on) */
+    int64_t kind_launches[AIS_N_KINDS]; /* timed brackets per class */
+    int64_t bound_passes;       /* second passes served by the per-tile bound on the blend instead of a streaming pass */
+    int64_t bitmap_batches;     /* batches whose BM25 side ran on the term-bitmap path (tf == 1 index) instead of per-tile records */
 } ais_stats;
 
 const char* ais_last_error(void);
@@ -138,6 +153,16 @@ int ais_vectors_device_ptr(ais_engine* e, int64_t n_docs, float** out_rows);
 int ais_load_bm25(ais_engine* e, const int64_t* post_ptr /*[n_terms+1]*/, const int32_t* post_doc,
                   const int32_t* post_tf, int32_t n_terms, int64_t n_docs, const double* idf /*[n_terms]*/,
                   const int64_t* doc_len /*[n_docs]*/, double avgdl);
+
+/* --- native reader of the reference's `bm25_corpus` file (host code, no GPU needed) --------------------------------
+ * genmodel.py:84-85 pickles a Python list of N dicts {term id: tf}; load_model() (webui.py:680) unpickles it into N
+ * Python dicts on every cold start.  These two calls stream the pickle's opcodes straight into doc-major CSR arrays
+ * instead: scan counts docs / entries, fill writes row_ptr [n_docs+1], term_ids [nnz], tfs [nnz] (host arrays; dict
+ * insertion order kept).  A pickle outside the list-of-int-dicts opcode subset returns AIS_ERR_UNSUPPORTED (the caller
+ * falls back to pickle.load); the message is in ais_pickle_last_error(). */
+int ais_pickle_csr_scan(const char* path, int64_t* out_n_docs, int64_t* out_nnz);
+int ais_pickle_csr_fill(const char* path, int64_t n_docs, int64_t nnz, int64_t* row_ptr, int32_t* term_ids, int32_t* tfs);
+const char* ais_pickle_last_error(void);
 
 /* --- index build: gen_and_save_bm25_index genmodel.py:51-99 on the GPU ------------------------ */
 /* From the docs' term-id sequences (doc-major CSR, csv tag order, repeats allowed; the host has already

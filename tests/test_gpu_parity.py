@@ -366,8 +366,12 @@ def test_topn_beyond_the_selector_is_not_truncated(prf_mode):
     t2i = idx.token2id
     infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
     texts = synth.generate_queries(idx, 5, seed=4)
-    eng = install(idx, prf_mode=prf_mode)
-    engines = [E.SearchEngine.from_index(idx, lo=lo, hi=hi) for lo, hi in (shard.shard_bounds(idx.n_docs, 2, r) for r in range(2))]
+    TH = 1e-13                       # (almost) no near-tie cut: the results really are longer than the selector's lists
+    P.consts["DIFF_FILTER_THRESH"] = TH
+    eng = install(idx, prf_mode=prf_mode, diff_filter_thresh=TH)
+    webui_api.DIFF_FILTER_THRESH = TH
+    engines = [E.SearchEngine.from_index(idx, lo=lo, hi=hi, diff_filter_thresh=TH)
+               for lo, hi in (shard.shard_bounds(idx.n_docs, 2, r) for r in range(2))]
     S = shard.ShardedSearch(engines, idx.n_docs)
     mode = E.PRF_STORED_ROWS if prf_mode == "stored_rows" else E.PRF_OFF
     n_long = 0
@@ -377,38 +381,101 @@ def test_topn_beyond_the_selector_is_not_truncated(prf_mode):
                 st = P.stages(text)
                 order = np.argsort(-st["final"], kind="stable")
                 srt = list(zip(order.tolist(), st["final"][order]))
-                want = capture(lambda: port.filter_searched_result(srt)[:topn])
+                want = capture(lambda: port.filter_searched_result(srt, TH)[:topn])
                 got = capture(lambda: eng.search([Q.make_query(text, t2i, infer)], topn, mode)[0])
                 sorted_fn = lambda s=srt: s
             else:
                 want = capture(P.find_similar_documents, text, topn)
                 got = capture(webui_api.find_similar_documents, text, topn)
                 sorted_fn = lambda t=text: P.find_sorted(t)
-            assert_same_or_filter_unstable(got, want, sorted_fn, 1e-6, topn, (text, topn))
+            assert_same_or_filter_unstable(got, want, sorted_fn, TH, topn, (text, topn))
             got2 = capture(lambda: S.search([Q.make_query(text, t2i, infer)], topn, mode)[0])
-            assert_same_or_filter_unstable(got2, want, sorted_fn, 1e-6, topn, ("sharded", text, topn))
+            assert_same_or_filter_unstable(got2, want, sorted_fn, TH, topn, ("sharded", text, topn))
             n_long += want[0] == "ok" and len(want[1]) > 1034
+    webui_api.DIFF_FILTER_THRESH = 1e-6
     assert n_long > 0, "no query returned more than the selector's 1024 + 10 docs: the test did not reach the long path"
+
     for e in engines:
         e.close()
 
 
-def test_pass2_tile_bound_equals_streaming_pass(monkeypatch):
-    """Pass 2 of the reference's collapsed re-query skips tiles by an upper bound on the blend R (select2.cuh,
-    collect_kernel<2, 1>); AIS_NO_TILE_BOUND=1 streams every doc instead.  Same results bit for bit, max R included."""
-    idx = synth.generate_index(60000, vocab_size=2000, seed=88)
+def test_bitmap_path_equals_record_path(monkeypatch):
+    """The BM25 side has two exact implementations: per-tile records from a posting walk (bm25_score_kernel; the default)
+    and term bitmaps (tf == 1 indexes, AIS_BM25_BITMAP=1; bm25_bitmap_kernel + bm25_tile_values: every pass re-derives the
+    values, IEEE division instead of the FMA-corrected one).  On a tf == 1 index both must return the same bits:
+    compute_bm25_scores (-inf masks included), combined scores, search results."""
+    idx = synth.generate_index(45000, vocab_size=1200, seed=23)
+    t2i = idx.token2id
+    infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
+    texts = synth.generate_queries(idx, 40, seed=12) + ["t3:+2 t12:+1 t9", "t0:-1 t1:-2 t2", "t13:0 t14:+0 t4:-0 t20:2"]
+    qs = [Q.make_query(t, t2i, infer) for t in texts]
+    many_terms = E.Query(qs[0].vec, np.arange(40, dtype=np.int32), np.r_[np.arange(1, 39, dtype=np.float64), 1003.0, -2.0])
+    qs.append(many_terms)                             # 40 terms: more than one group of four in flight
+    P = port.OraclePort(idx)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("AIS_BM25_BITMAP", flag)
+        eng = E.SearchEngine.from_index(idx, max_batch=len(qs))
+        eng.reset_stats()
+        res = eng.search_raw(qs, 100, E.PRF_STORED_ROWS)
+        fins = [eng.debug_read("fin", j) for j in (0, 7, len(qs) - 1)]
+        bm = [eng.bm25_scores(q.term_ids, q.weights) for q in qs[-6:]]
+        assert (eng.stats()["bitmap_batches"] > 0) == (flag == "1")
+        out[flag] = (res, fins, bm)
+        eng.close()
+    for x, y in zip(out["0"][0][:4], out["1"][0][:4]):
+        assert np.array_equal(x, y)
+    for x, y in zip(out["0"][1] + out["0"][2], out["1"][1] + out["1"][2]):
+        assert np.array_equal(x, y, equal_nan=True)
+    for q, got in zip(qs[-6:], out["0"][2]):         # and both equal the oracle's compute_bm25_scores, bit for bit
+        want = P.bm25_scores(dict(zip(q.term_ids.tolist(), q.weights.tolist())))
+        assert np.array_equal(got, want)
+
+
+def test_fma_corrected_division_equals_ieee_division(monkeypatch):
+    """bm25 / max(bm25) (webui.py:379-380, fp64) runs as RN(1/max) + two FMAs (finals.cuh ddiv_by_max); AIS_IEEE_DIV=1
+    switches to __ddiv_rn.  Every combined score of every doc and the search results must be the same bits."""
+    idx = synth.generate_index(60000, vocab_size=900, seed=29)
+    t2i = idx.token2id
+    infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
+    qs = [Q.make_query(t, t2i, infer) for t in synth.generate_queries(idx, 32, seed=21)]
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("AIS_IEEE_DIV", flag)
+        eng = E.SearchEngine.from_index(idx, max_batch=len(qs))
+        res = eng.search_raw(qs, 100, E.PRF_STORED_ROWS)
+        out[flag] = (res, [eng.debug_read("fin", j) for j in range(len(qs))])
+        eng.close()
+    for x, y in zip(out["0"][0][:4], out["1"][0][:4]):
+        assert np.array_equal(x, y)
+    for x, y in zip(out["0"][1], out["1"][1]):
+        assert np.array_equal(x, y, equal_nan=True)
+
+
+def test_pass2_tile_skip_equals_full_pass(monkeypatch):
+    """Pass 2 of the reference's collapsed re-query: the maxima kernel skips tiles whose upper bound on the blend R stays
+    below a threshold taken from the pass-1 candidates (select2.cuh, rerank_max_kernel<1>; default), visits every tile
+    (AIS_NO_TILE_SKIP=1), or the collect itself applies the bound (AIS_TILE_BOUND=1, collect_kernel<2, 1>); and the generic
+    streaming kernel (AIS_NO_RERANK_MAX=1, segmax_kernel<2>).  Same results bit for bit, max R included."""
+    idx = synth.generate_index(300000, vocab_size=2000, seed=88, rows="random")
     t2i = idx.token2id
     infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
     qs = [Q.make_query(q, t2i, infer) for q in synth.generate_queries(idx, 24, seed=6)]
     out = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("AIS_NO_TILE_BOUND", flag)
+    for name, env in (("skip", {}), ("full", {"AIS_NO_TILE_SKIP": "1"}), ("collect_bound", {"AIS_TILE_BOUND": "1"}),
+                      ("generic", {"AIS_NO_RERANK_MAX": "1"})):
+        for k in ("AIS_NO_TILE_SKIP", "AIS_TILE_BOUND", "AIS_NO_RERANK_MAX"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         eng = E.SearchEngine.from_index(idx, max_batch=24)
-        out[flag] = [eng.search_raw(qs, topn, E.PRF_STORED_ROWS) for topn in (100, 800)]
+        out[name] = [eng.search_raw(qs, topn, E.PRF_STORED_ROWS) for topn in (100, 800)]
+        assert (eng.stats()["bound_passes"] > 0) == (name in ("skip", "collect_bound")), name
         eng.close()
-    for a, b in zip(out["0"], out["1"]):
-        for x, y in zip(a[:4], b[:4]):
-            assert np.array_equal(x, y)
+    for name in ("full", "collect_bound", "generic"):
+        for a, b in zip(out["skip"], out[name]):
+            for x, y in zip(a[:4], b[:4]):
+                assert np.array_equal(x, y), name
 
 
 def test_clustered_top_docs_overflow_the_streaming_select():
