@@ -122,7 +122,8 @@ struct Bm25Args {
 // rec_base[q] + tile_off[q][tile] of the record pools.  tile_off = the number of postings of the query's terms that lie
 // BEFORE the tile (read off the slice table): a tile has at most as many records as postings, so the regions never
 // overlap and no cursor is shared (a per-query atomic cursor serialised ~10 M atomics per batch on 256 addresses).
-__global__ void __launch_bounds__(BM25_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(BM25_THREADS, MINB)
 bm25_score_kernel(Bm25Args A) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -251,53 +252,60 @@ bm25_score_kernel(Bm25Args A) {
     }
 
     // ---- record: bitmap, then values + positions compacted in doc order, and the maximum over the tile ----
-    // webui.py:160,168: excluded hit, or a required term missing -> -inf (absorbing under +=)
+    // webui.py:160,168: excluded hit, or a required term missing -> -inf (absorbing under +=).  This part runs for every
+    // (tile, query): 32-bit indices, no fmax (the values are finite or -inf, never NaN: idf, K_d and the weights are finite).
+    const int n_valid = (int)(hi - lo);
     double v[BM25_SUB / 32];
     uint32_t m[BM25_SUB / 32];
     int n_rec = 0;
+    if (has_req) {
+#pragma unroll
+        for (int u = 0; u < BM25_SUB / 32; ++u) {
+            const int l = u * 32 + lane;
+            v[u] = reqc[l] != n_required ? -INFINITY : acc[l];         // webui.py:168: a required term is missing
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < BM25_SUB / 32; ++u) v[u] = acc[u * 32 + lane];
+    }
 #pragma unroll
     for (int u = 0; u < BM25_SUB / 32; ++u) {
-        const int l = u * 32 + lane;
-        double x = acc[l];
-        if (has_req && reqc[l] != n_required) x = -INFINITY;      // webui.py:168: a required term is missing
-        v[u] = x;
-        const bool in = lo + l < hi;
-        if (A.dense_out && in) A.dense_out[(int64_t)qi * A.ld + lo + l] = x;
-        m[u] = __ballot_sync(0xffffffffu, in && x != untouched);  // NaN never appears: idf, K_d and the weights are finite
+        m[u] = __ballot_sync(0xffffffffu, u * 32 + lane < n_valid && v[u] != untouched);
         n_rec += __popc(m[u]);
     }
+    if (A.dense_out) {
+        double* dq = A.dense_out + (int64_t)qi * A.ld + lo;
+#pragma unroll
+        for (int u = 0; u < BM25_SUB / 32; ++u)
+            if (u * 32 + lane < n_valid) dq[u * 32 + lane] = v[u];
+    }
     const unsigned int off = rec_off;
-    double* rv = A.rec_val + A.rec_base[qi] + off;
-    uint8_t* rp = A.rec_pos + A.rec_base[qi] + off;
+    const int64_t rb = A.rec_base[qi] + off;
+    double* rv = A.rec_val + rb;
+    uint8_t* rp = A.rec_pos + rb;
+    const unsigned lt = (1u << lane) - 1u;
     double bd = -INFINITY;                                        // maximum in the double domain, one key at the end
-    bool any = false;
     int prefix = 0;
     uint32_t mine = 0u;                                           // lane u keeps word u of the bitmap
 #pragma unroll
     for (int u = 0; u < BM25_SUB / 32; ++u) {
         if ((m[u] >> lane) & 1u) {
-            const int slot = prefix + __popc(m[u] & ((1u << lane) - 1u));
+            const int slot = prefix + __popc(m[u] & lt);
             rv[slot] = v[u];
             rp[slot] = (uint8_t)(u * 32 + lane);
-            bd = fmax(bd, v[u]);
-            any = true;
+            bd = v[u] > bd ? v[u] : bd;
         }
         prefix += __popc(m[u]);
         mine = lane == u ? m[u] : mine;
     }
     if (lane < 8) hdr[lane] = mine;
     if (lane == 0) A.tile_off[(int64_t)qi * A.tile_ld + sub] = off;
-    if (n_rec < (int)(hi - lo)) {                                 // some doc keeps the default
-        bd = fmax(bd, untouched);
-        any = true;
+    uint64_t best = dkey(bd);                                     // dkey(-inf) is a valid (smallest real) key
+    if (n_rec < n_valid) {                                        // some doc keeps the default
+        const uint64_t ku = dkey(untouched);
+        best = ku > best ? ku : best;
     }
-    uint64_t best = any ? dkey(bd) : KEY_EMPTY;
-    {   // 64-bit warp maximum with two redux.sync
-        const uint32_t bh = (uint32_t)(best >> 32), bl = (uint32_t)best;
-        const uint32_t mh = __reduce_max_sync(0xffffffffu, bh);
-        const uint32_t ml = __reduce_max_sync(0xffffffffu, bh == mh ? bl : 0u);
-        best = ((uint64_t)mh << 32) | ml;
-    }
+    best = warp_max_u64_redux(best);
     if (lane == 0 && best > *(volatile uint64_t*)&A.max_keys[qi])
         atomicMax(reinterpret_cast<unsigned long long*>(&A.max_keys[qi]), (unsigned long long)best);
 }
@@ -389,7 +397,6 @@ struct CombineArgs {
     int64_t n_sub;
     uint64_t* seg_max; int seg_stride; int tiles_per_seg;     // seg_max[q * seg_stride + tile / tiles_per_seg]
     uint64_t* tile_max;                                        // tile_max[q][tile]: best combined key of the tile
-    double* rec_out;                                           // records path: the record pool, rewritten in place (see FinSrc::rec_scaled)
 };
 
 // After the global maxima are known.  One warp per (tile, query): the best combined score of the tile
@@ -399,85 +406,80 @@ struct CombineArgs {
 // of the largest (wd >= 0) dot score among them: one FMNMX per doc.  Docs WITH a record (~45 of 256) take the exact
 // formula, one doc per lane, reading the compacted record (value + position) - the dot score comes from the tile's 1 KB
 // the warp has just pulled through L1.
-__global__ void __launch_bounds__(BM25C_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(BM25C_THREADS, MINB)
 bm25_combine_kernel(CombineArgs A) {
     const FinSrc& S = A.S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t sub = (int64_t)blockIdx.x * BM25C_WARPS + warp;
-    if (sub >= A.n_sub) return;
+    const int sub = blockIdx.x * BM25C_WARPS + warp;               // 32-bit tile index: n_sub < 2^23 (shards hold < 2^31 docs)
+    if (sub >= (int)A.n_sub) return;
     const int qi = blockIdx.y;
-    const int64_t lo = sub * BM25_SUB;
-    const int64_t hi = (lo + BM25_SUB < S.n) ? lo + BM25_SUB : S.n;
-    const float* simq = S.sim + (int64_t)qi * S.ld;
+    const int64_t lo = (int64_t)sub * BM25_SUB;
+    const int n_valid = (int)((lo + BM25_SUB < S.n ? lo + BM25_SUB : S.n) - lo);
+    const float* simt = S.sim + (int64_t)qi * S.ld + lo;           // the tile's dot scores
+    const int64_t tq = (int64_t)qi * S.tile_ld + sub;
 
     float sv[BM25_SUB / 32];
 #pragma unroll
-    for (int u = 0; u < BM25_SUB / 32; ++u) {
-        const int64_t d = lo + u * 32 + lane;
-        sv[u] = d < hi ? simq[d] : 0.0f;
-    }
-    const uint4* hp = reinterpret_cast<const uint4*>(S.tile_hdr + ((int64_t)qi * S.tile_ld + sub) * 8);
+    for (int u = 0; u < BM25_SUB / 32; ++u) sv[u] = u * 32 + lane < n_valid ? simt[u * 32 + lane] : 0.0f;
+    const uint4* hp = reinterpret_cast<const uint4*>(S.tile_hdr + tq * 8);
     const uint4 h0 = hp[0], h1 = hp[1];
-    const unsigned int off = S.tile_off[(int64_t)qi * S.tile_ld + sub];
-    const int64_t rbase = S.rec_base[qi] + off;
+    const int64_t rbase = S.rec_base[qi] + S.tile_off[tq];
     const QNorm c = S.qnorm(qi);
     const uint32_t w[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
     int n_rec = 0;
 #pragma unroll
     for (int u = 0; u < 8; ++u) n_rec += __popc(w[u]);
     // the first 64 records are fetched before anything depends on them
+    const double* rvp = S.rec_val + rbase;
+    const uint8_t* rpp = S.rec_pos + rbase;
     double pv[2];
     int pp[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int i = 32 * r + lane;
-        pv[r] = i < n_rec ? S.rec_val[rbase + i] : 0.0;
-        pp[r] = i < n_rec ? (int)S.rec_pos[rbase + i] : 0;
+        pv[r] = i < n_rec ? rvp[i] : 0.0;
+        pp[r] = i < n_rec ? (int)rpp[i] : 0;
     }
 
-    // docs without a record: the extreme dot score among them
+    // docs without a record: the extreme dot score among them (NaN dot scores - NaN rows - are caught by x != x)
     const bool up = !(S.wd < 0.0f);
     float ext = up ? -INFINITY : INFINITY;
     bool nan_seen = false;
 #pragma unroll
     for (int u = 0; u < BM25_SUB / 32; ++u) {
-        const bool plain = !((w[u] >> lane) & 1u) && lo + u * 32 + lane < hi;
-        const float x = sv[u];
-        nan_seen = nan_seen || (plain && x != x);
-        if (plain) ext = up ? fmaxf(ext, x) : fminf(ext, x);
+        const bool plain = !((w[u] >> lane) & 1u) && u * 32 + lane < n_valid;
+        const float x = plain ? sv[u] : ext;
+        nan_seen = nan_seen || x != x;
+        ext = up ? fmaxf(ext, x) : fminf(ext, x);
     }
     double fbest = -INFINITY;
     bool any = false;
-    if (n_rec < (int)(hi - lo)) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float y = __shfl_xor_sync(0xffffffffu, ext, o);
-            ext = up ? fmaxf(ext, y) : fminf(ext, y);
-        }
-        fbest = S.blend(c.wb_dflt, S.sim_norm(c, ext));                               // webui.py:383
+    if (n_rec < n_valid) {                                         // warp-uniform
+        // order-preserving integer image: one redux per direction instead of five shuffle rounds
+        const uint32_t k = fkey(ext);
+        const uint32_t kk = up ? __reduce_max_sync(0xffffffffu, k) : __reduce_min_sync(0xffffffffu, k);
+        fbest = S.blend(c.wb_dflt, S.sim_norm(c, fkey_inv(kk)));                      // webui.py:383
         nan_seen = nan_seen || fbest != fbest;
         any = true;
     }
     // docs with a record: exact, one per lane
-    auto exact = [&](double val, int pos, int64_t slot) {
-        const float x = simq[lo + pos];
-        const double wbb = __dmul_rn(S.wb, S.bm25_norm(c, val));
-        A.rec_out[slot] = wbb;                        // in place: the later passes read BM25_WEIGHT * (value / max) directly
-        const double f = S.blend(wbb, S.sim_norm(c, x));
+    auto exact = [&](double val, int pos) {
+        const double f = S.blend(__dmul_rn(S.wb, S.bm25_norm(c, val)), S.sim_norm(c, simt[pos]));
         nan_seen = nan_seen || f != f;
-        fbest = fmax(fbest, f);
+        fbest = f > fbest ? f : fbest;
         any = true;
     };
-    if (lane < n_rec) exact(pv[0], pp[0], rbase + lane);
-    if (32 + lane < n_rec) exact(pv[1], pp[1], rbase + 32 + lane);
-    for (int i = 64 + lane; i < n_rec; i += 32) exact(S.rec_val[rbase + i], (int)S.rec_pos[rbase + i], rbase + i);
+    if (lane < n_rec) exact(pv[0], pp[0]);
+    if (32 + lane < n_rec) exact(pv[1], pp[1]);
+    for (int i = 64 + lane; i < n_rec; i += 32) exact(rvp[i], (int)rpp[i]);
     uint64_t best = any ? dkey(fbest) : KEY_EMPTY;
     if (nan_seen) best = KEY_NAN;                                  // e.g. weight 0 x -inf
-    best = warp_max_u64(best);
+    best = warp_max_u64_redux(best);
     if (lane == 0) {
-        A.tile_max[(int64_t)qi * S.tile_ld + sub] = best;
+        A.tile_max[tq] = best;
         if (best != KEY_EMPTY)
-            atomicMax(reinterpret_cast<unsigned long long*>(&A.seg_max[(size_t)qi * A.seg_stride + (int)(sub / A.tiles_per_seg)]),
+            atomicMax(reinterpret_cast<unsigned long long*>(&A.seg_max[(size_t)qi * A.seg_stride + sub / A.tiles_per_seg]),
                       (unsigned long long)best);
     }
 }

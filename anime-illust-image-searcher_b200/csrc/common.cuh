@@ -136,6 +136,13 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// 64-bit warp maximum with two redux.sync instead of five shuffle rounds
+__device__ __forceinline__ uint64_t warp_max_u64_redux(uint64_t v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((uint64_t)mh << 32) | ml;
+}
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -158,6 +158,7 @@ struct ais_engine {
     int bm25_t_cap = 1;
     Buf q_nreq;                // [qt_cap] number of required terms per query
     Buf q_idf;                 // [qt_cap][MAX_TERMS] idf of every query term
+    Buf qnorm_tab;  bool qnorm_ready = false;   // [qt_cap] per-query constants of the combine, formed once per batch (finals.cuh QNorm)
     Buf tile_hdr;              // [qt_cap][tile_ld][8] bitmap of the docs with a BM25 record (bm25.cuh)
     Buf tile_off;              // [qt_cap][tile_ld] first record slot of the tile, relative to rec_base[q]
     Buf rec_val, rec_pos;      // record pools: fp64 values / positions inside the tile
@@ -166,9 +167,10 @@ struct ais_engine {
     Buf term_bits, slot_terms;  // bitmap path: presence bitmaps [n_slots][n_tiles][32 B] of the batch's distinct terms / their ids
     int32_t* h_slot_terms = nullptr;
     int n_slots = 0;
-    bool rec_scaled = false;    // current batch, records path: the combine pass has rewritten the records (FinSrc::rec_scaled)
     bool use_bits = false;      // current batch: BM25 from the term bitmaps (tf == 1 index, bitmaps fit) - else per-tile records
     bool ieee_div = false;      // AIS_IEEE_DIV=1: __ddiv_rn for bm25 / max (cross-check of the FMA-corrected quotient)
+    int combine_occ = 5;        // AIS_COMBINE_OCC: the same for bm25_combine_kernel (5 / 6 / 8)
+    int score_occ = 6;          // AIS_SCORE_OCC: resident 256-thread blocks per SM the score kernel is compiled for (4 / 5 / 6)
     bool want_bits = false;     // AIS_BM25_BITMAP=1: the bitmap path where it applies (default: per-tile records)
     int64_t bitmap_cap_bytes = 4LL << 30;     // AIS_BM25_BITMAP_MB
     int64_t bitmap_batches = 0;
@@ -331,6 +333,7 @@ int ensure_work(ais_engine* e) {
     TRY(dev_alloc(e, e->tile_off, (size_t)q * tl * sizeof(uint32_t)));
     TRY(dev_alloc(e, e->q_nreq, (size_t)q * sizeof(int32_t)));
     TRY(dev_alloc(e, e->q_idf, (size_t)q * MAX_TERMS * sizeof(double)));
+    TRY(dev_alloc(e, e->qnorm_tab, (size_t)q * sizeof(QNorm)));
     TRY(dev_alloc(e, e->rec_base, (size_t)q * sizeof(int64_t)));
     TRY(dev_alloc(e, e->slot_terms, (size_t)q * MAX_TERMS * sizeof(int32_t)));
     TRY(dev_alloc(e, e->col_lo, (size_t)tl * sizeof(float)));
@@ -677,7 +680,6 @@ FinSrc fin_src(const ais_engine* e, const double* d_maxes) {
     S.sim = e->sim.as<float>();
     S.ld = e->ld;
     S.use_bits = e->use_bits ? 1 : 0;
-    S.rec_scaled = e->rec_scaled ? 1 : 0;
     S.ieee_div = e->ieee_div ? 1 : 0;
     S.B.bits = e->term_bits.as<uint8_t>();
     S.B.n_tiles = (e->n() + SEL_TILE - 1) / SEL_TILE;
@@ -693,6 +695,7 @@ FinSrc fin_src(const ais_engine* e, const double* d_maxes) {
     S.rec_base = e->rec_base.as<int64_t>();
     S.maxes = d_maxes;
     S.n_required = e->q_nreq.as<int32_t>();
+    S.qtab = (e->qnorm_ready && d_maxes == e->cur_maxes) ? e->qnorm_tab.as<QNorm>() : nullptr;
     S.wb = e->p.bm25_weight;
     S.wd = (float)e->p.doc2vec_weight;
     S.n = e->n();
@@ -778,7 +781,11 @@ int launch_bm25_max(ais_engine* e, int nq, double* dense_out) {
     Bm25Args a = bm25_args(e, n_sub);
     a.max_keys = e->maxb_key.as<uint64_t>();
     a.dense_out = dense_out;
-    bm25_score_kernel<<<dim3((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq), BM25_THREADS, BM25_SMEM, e->stream>>>(a);
+    const dim3 gs((unsigned)((n_sub + BM25_WARPS - 1) / BM25_WARPS), (unsigned)nq);
+    if (e->score_occ >= 8) bm25_score_kernel<8><<<gs, BM25_THREADS, BM25_SMEM, e->stream>>>(a);
+    else if (e->score_occ >= 6) bm25_score_kernel<6><<<gs, BM25_THREADS, BM25_SMEM, e->stream>>>(a);
+    else if (e->score_occ == 5) bm25_score_kernel<5><<<gs, BM25_THREADS, BM25_SMEM, e->stream>>>(a);
+    else bm25_score_kernel<4><<<gs, BM25_THREADS, BM25_SMEM, e->stream>>>(a);
     LAUNCHED(e);
     return AIS_OK;
 }
@@ -854,7 +861,8 @@ int local_select(ais_engine* e, int mode, int nq, int k, uint64_t* d_keys, int64
     if (bound) e->bound_passes++;
     // pass 2 on the records path: rerank_max_kernel (seeds not excluded from its segment maxima -> `depth` more segments
     // counted by the threshold); `skip`: with the tile bound on R, from the threshold of the pass-1 candidates
-    const bool records2 = mode == 2 && !bound && !e->use_bits && !e->ext_fin && e->rec_scaled && !getenv("AIS_NO_RERANK_MAX");
+    const bool fast = !e->use_bits && !e->ext_fin && !getenv("AIS_NO_RERANK_MAX");     // records path: two-class tile evaluation
+    const bool records2 = mode == 2 && !bound && fast;
     const bool skip = records2 && e->ub_valid && !e->no_skip;
     if (n > 0 && !bound) {
         ProfScope prof(e, AIS_KIND_COMBINE);
@@ -865,13 +873,15 @@ int local_select(ais_engine* e, int mode, int nq, int k, uint64_t* d_keys, int64
             c.n_sub = a.n_tiles;
             c.seg_max = a.seg_max; c.seg_stride = SEG_MAX; c.tiles_per_seg = a.tiles_per_seg;
             c.tile_max = a.tile_max;
-            c.rec_out = e->rec_val.as<double>();
             if (e->use_bits)
                 bm25_combine_bits_kernel<<<dim3((unsigned)a.n_tiles, (unsigned)((nq + BITQ_WARPS - 1) / BITQ_WARPS)), 32 * BITQ_WARPS, 0, e->stream>>>(c, nq);
-            else
-                bm25_combine_kernel<<<dim3((unsigned)((a.n_tiles + BM25C_WARPS - 1) / BM25C_WARPS), (unsigned)nq), BM25C_THREADS, 0, e->stream>>>(c);
+            else {
+                const dim3 gc((unsigned)((a.n_tiles + BM25C_WARPS - 1) / BM25C_WARPS), (unsigned)nq);
+                if (e->combine_occ >= 8) bm25_combine_kernel<8><<<gc, BM25C_THREADS, 0, e->stream>>>(c);
+                else if (e->combine_occ >= 6) bm25_combine_kernel<6><<<gc, BM25C_THREADS, 0, e->stream>>>(c);
+                else bm25_combine_kernel<5><<<gc, BM25C_THREADS, 0, e->stream>>>(c);
+            }
             LAUNCHED(e);
-            if (!e->use_bits) { e->rec_scaled = true; a.S.rec_scaled = 1; }
         } else {
             if (mode == 2) {                                 // the tile table of R is separate: pass 1's stays valid
                 TRY(dev_alloc(e, e->tile_max2, (size_t)e->qt_cap * e->tile_ld * sizeof(uint64_t)));
@@ -880,7 +890,7 @@ int local_select(ais_engine* e, int mode, int nq, int k, uint64_t* d_keys, int64
             const dim3 g1((unsigned)a.n_seg, (unsigned)((nq + SEG_WARPS - 1) / SEG_WARPS));
             if (mode == 1) segmax_kernel<1><<<g1, 32 * SEG_WARPS, 0, e->stream>>>(a, nq);
             else if (records2) {                             // records path: the light pass over the scaled records
-                const dim3 g2((unsigned)a.n_tiles, (unsigned)((nq + SEG_WARPS - 1) / SEG_WARPS));
+                const dim3 g2((unsigned)((a.n_tiles + 31) / 32), (unsigned)((nq + SEG_WARPS - 1) / SEG_WARPS));
                 if (skip) {                                  // threshold from the pass-1 candidates first: tiles that cannot reach it are skipped
                     rerank_threshold_kernel<<<nq, 256, 0, e->stream>>>(e->p1_keys.as<uint64_t>(), e->p1_ids.as<int64_t>(), e->p1_k, a, k);
                     LAUNCHED(e);
@@ -907,8 +917,10 @@ int local_select(ais_engine* e, int mode, int nq, int k, uint64_t* d_keys, int64
         int64_t cb = (a.n_tiles + COLLECT_THREADS - 1) / COLLECT_THREADS;     // one lane per tile
         if (cb > 2LL * e->sm_count) cb = 2LL * e->sm_count;
         const dim3 g3((unsigned)cb, (unsigned)nq);
-        if (mode != 2) collect_kernel<1, 0><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
-        else if (bound) collect_kernel<2, 1><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        if (bound) collect_kernel<2, 1><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        else if (fast && mode != 2) collect_fast_kernel<1><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        else if (fast) collect_fast_kernel<2><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
+        else if (mode != 2) collect_kernel<1, 0><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
         else collect_kernel<2, 0><<<g3, COLLECT_THREADS, 0, e->stream>>>(a);
         LAUNCHED(e);
     }
@@ -953,7 +965,7 @@ int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
     e->rer_column = false;
     e->ext_fin = false;
     e->bound_ok = false;
-    e->rec_scaled = false;
+    e->qnorm_ready = false;
     e->p1_k = 0;
     return AIS_OK;
 }
@@ -963,6 +975,12 @@ int do_score(ais_engine* e, const ais_query* qs, int nq, double* d_maxes) {
 // the pass-2 threshold of the collapsed re-query starts from it.
 int do_combine(ais_engine* e, int nq, const double* d_maxes, int k, uint64_t* d_keys, int64_t* d_ids) {
     e->cur_maxes = d_maxes;
+    e->qnorm_ready = false;
+    if (!e->ext_fin) {                                   // the per-query constants of webui.py:376-383, once per batch
+        qnorm_kernel<<<(nq + 63) / 64, 64, 0, e->stream>>>(fin_src(e, d_maxes), nq, e->qnorm_tab.as<QNorm>());
+        LAUNCHED(e);
+        e->qnorm_ready = true;
+    }
     TRY(local_select(e, e->ext_fin ? 1 : 0, nq, k, d_keys, d_ids));
     TRY(dev_alloc(e, e->p1_keys, (size_t)e->qt_cap * SEL_KMAX * sizeof(uint64_t)));
     TRY(dev_alloc(e, e->p1_ids, (size_t)e->qt_cap * SEL_KMAX * sizeof(int64_t)));
@@ -1430,6 +1448,8 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
 
     if (const char* sd = getenv("AIS_SELECT_DEPTH")) e->sel_deep = atoi(sd);
     if (const char* fr = getenv("AIS_BM25_BITMAP")) e->want_bits = atoi(fr) != 0;
+    if (const char* so = getenv("AIS_SCORE_OCC")) e->score_occ = atoi(so);
+    if (const char* co = getenv("AIS_COMBINE_OCC")) e->combine_occ = atoi(co);
     if (const char* dv = getenv("AIS_IEEE_DIV")) e->ieee_div = atoi(dv) != 0;
     if (const char* bm = getenv("AIS_BM25_BITMAP_MB")) e->bitmap_cap_bytes = (int64_t)atoll(bm) << 20;
 
@@ -1443,7 +1463,7 @@ int ais_destroy(ais_engine* e) {
     if (!e) return AIS_OK;
     DeviceGuard g(e->device);
     cudaStreamSynchronize(e->stream);
-    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->g1, &e->doc_len, &e->sim, &e->scratch64, &e->fin_ext, &e->p1_keys, &e->p1_ids, &e->q_idf, &e->tile_off, &e->rec_val, &e->rec_pos, &e->rec_base, &e->post_len, &e->kd_tab, &e->g1_tab, &e->term_bits, &e->slot_terms, &e->tile_max2, &e->col_lo, &e->col_hi,
+    for (Buf* b : {&e->rows, &e->post_ptr, &e->post_doc, &e->post_tf, &e->idf, &e->kd, &e->g1, &e->doc_len, &e->sim, &e->scratch64, &e->fin_ext, &e->p1_keys, &e->p1_ids, &e->q_idf, &e->tile_off, &e->rec_val, &e->rec_pos, &e->rec_base, &e->qnorm_tab, &e->post_len, &e->kd_tab, &e->g1_tab, &e->term_bits, &e->slot_terms, &e->tile_max2, &e->col_lo, &e->col_hi,
                    &e->rer, &e->d_q, &e->d_q2, &e->d_qt, &e->maxs_key, &e->maxb_key, &e->maxr_key, &e->maxes_own, &e->maxr_own,
                    &e->top_ids, &e->top_scores, &e->status, &e->rows_own, &e->blk_keys, &e->blk_ids, &e->grp_keys, &e->grp_ids,
                    &e->cand_keys, &e->cand_ids, &e->rest_keys, &e->rest_ids, &e->rest_count, &e->out_ids, &e->out_scores,

@@ -131,8 +131,6 @@ struct FinSrc {
     const float* sim; int64_t ld;                 // [q][ld] dot scores
     int use_bits;               // 1: BM25 from the term bitmaps (B), 0: from the per-tile records below
     int ieee_div;               // 1: bm25 / max with __ddiv_rn instead of the FMA-corrected quotient (AIS_IEEE_DIV=1; cross-check)
-    int rec_scaled;             // records path: 1 once bm25_combine_kernel has replaced the raw BM25 values of the records by
-                                // BM25_WEIGHT * (value / max) in place - the later passes then skip the division
     BitSrc B;
     const uint32_t* tile_hdr;                     // [q][tile_ld][8] bitmap of the docs with a record
     const uint32_t* tile_off;                     // [q][tile_ld] first record slot of the tile, relative to rec_base[q]
@@ -140,10 +138,15 @@ struct FinSrc {
     const double* rec_val; const uint8_t* rec_pos; const int64_t* rec_base;   // pools; rec_base [q]
     const double* maxes;        // [q][2] {max bm25, max dot} over ALL docs of ALL shards
     const int32_t* n_required;  // [q]
+    const QNorm* qtab;          // [q] the constants below, formed once per batch by qnorm_kernel (null: formed per call)
     double wb; float wd;        // BM25_WEIGHT (fp64 multiply), DOC2VEC_WEIGHT (fp32 multiply)
     int64_t n;
 
     __device__ __forceinline__ QNorm qnorm(int qi) const {
+        if (qtab) return qtab[qi];
+        return qnorm_compute(qi);
+    }
+    __device__ __forceinline__ QNorm qnorm_compute(int qi) const {
         QNorm c;
         c.maxb = maxes[2 * qi];
         c.maxs = (float)maxes[2 * qi + 1];
@@ -171,6 +174,13 @@ struct FinSrc {
         return __dadd_rn(bm25n_or_wb_product, (double)__fmul_rn(wd, simn));
     }
 };
+
+// the per-query constants once per batch (every tile of every pass would otherwise re-derive them: two reciprocals, the
+// exponent-window tests)
+__global__ void qnorm_kernel(FinSrc S, int nq, QNorm* __restrict__ out) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi < nq) out[qi] = S.qnorm_compute(qi);
+}
 
 // Combined scores of the docs  tile * 256 + 32 * u + lane  (u = 0..7) of query qi, one warp per call.
 // Docs beyond n get -inf and a cleared bit in `valid` (bit u).
@@ -219,10 +229,7 @@ __device__ __forceinline__ void tile_finals(const FinSrc& S, int qi, int64_t til
     for (int u = 0; u < FIN_U; ++u) {
         const int64_t d = lo + 32 * u + lane;
         double wbb = c.wb_dflt;
-        if ((w[u] >> lane) & 1u) {
-            const double rv = rec[prefix + __popc(w[u] & lt)];
-            wbb = S.rec_scaled ? rv : __dmul_rn(S.wb, S.bm25_norm(c, rv));
-        }
+        if ((w[u] >> lane) & 1u) wbb = __dmul_rn(S.wb, S.bm25_norm(c, rec[prefix + __popc(w[u] & lt)]));
         prefix += __popc(w[u]);
         const bool in = d < S.n;
         f[u] = in ? S.blend(wbb, S.sim_norm(c, sv[u])) : -INFINITY;

@@ -65,14 +65,6 @@ struct SelectArgs {        // everything the kernels share
     }
 };
 
-// 64-bit warp maximum with two redux.sync instead of five shuffle rounds
-__device__ __forceinline__ uint64_t warp_max_u64_redux(uint64_t v) {
-    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
-    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-    return ((uint64_t)mh << 32) | ml;
-}
-
 // scores of one tile for the select kernels: MODE 1 the combined scores, MODE 2 the blend R
 template <int MODE>
 __device__ __forceinline__ void tile_scores(const SelectArgs& a, const Rerank& rk, int qi, int64_t tile, int lane,
@@ -157,47 +149,24 @@ segmax_kernel(SelectArgs a, int nq) {
         atomicMax(reinterpret_cast<unsigned long long*>(&a.max_all[qi]), (unsigned long long)all_best);
 }
 
-// ---- 1b. pass 2 on the records path: tile / segment maxima of the blend R in one light pass ---------------------------
-// R = wo * final + wr * rer (webui.py:208) for every doc, from the dot score (4 B), the re-query score (the shared column
-// or the query's dense array, 4 B) and the tile's BM25 records as bm25_combine_kernel left them (BM25_WEIGHT * value / max,
-// no division left).  One warp per (tile, query), block = one tile x 8 queries (the column comes through L1 once for the
-// eight).  Docs without a record take ~12 instructions each straight from registers; the ~45 docs with one are handled
-// compactly, one per lane, through their stored positions.  The PRF seeds are NOT excluded here (webui.py:217 drops them
-// from the candidates): the caller asks the segment-maximum threshold for `depth` more segments instead, which keeps it
-// a valid lower bound - at most `depth` of the counted maxima can be seeds.
-// BOUND = 1 (the reference's collapsed re-query with non-negative blend weights): a.thr holds a lower bound T of the
-// k-th best R of this shard (rerank_threshold_kernel).  A tile whose upper bound - the blend of its best COMBINED score
-// (pass 1's tile table) with its extreme column value, every rounding monotone - stays below T holds no candidate and not
-// the maximum of R either: it is skipped after two 8-byte loads.  Measured on the benchmark: 12 % of the tiles remain.
-template <int BOUND>
-__global__ void __launch_bounds__(32 * SEG_WARPS)
-rerank_max_kernel(SelectArgs a, int nq, const uint64_t* __restrict__ tile_max_fin) {
+// ---- records path: the scores of one tile in two classes ----------------------------------------------------------
+// Docs WITHOUT a BM25 record share the query's default BM25 value: their combined score needs the dot score only (~12
+// instructions per doc, straight from registers).  The ~45 docs WITH a record are handled compactly, one per lane,
+// through the stored (value, position) pairs - no per-doc bitmap-prefix lookup, no dynamic register indexing.
+// fn(valid, score, l) is called warp-uniformly (every lane, every round): l = doc index inside the tile.
+// MODE 1: combined score (webui.py:376-383); MODE 2: the blend R with the re-query score (webui.py:208).
+template <int MODE, typename F>
+__device__ __forceinline__ void tile_two_class(const SelectArgs& a, const Rerank& rk, int qi, int64_t tile, int lane, F&& fn) {
     const FinSrc& S = a.S;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t tile = blockIdx.x;
-    const int qi = blockIdx.y * SEG_WARPS + warp;
-    if (qi >= nq) return;
     const int64_t lo = tile * SEL_TILE;
     const int64_t hi = lo + SEL_TILE < a.n ? lo + SEL_TILE : a.n;
-    const Rerank rk = a.rerank(qi);
-    if (BOUND == 1) {
-        uint64_t bound = tile_max_fin[(int64_t)qi * S.tile_ld + tile];
-        if (bound != KEY_EMPTY && bound < KEY_NAN) {
-            const float cx = rk.cq < 0.0f ? a.col_lo[tile] : a.col_hi[tile];
-            bound = dkey(rk.blend(dkey_inv(bound), cx));
-        }
-        if (bound < a.thr[qi]) {                                   // warp-uniform
-            if (lane == 0) a.tile_max[(int64_t)qi * S.tile_ld + tile] = KEY_EMPTY;
-            return;
-        }
-    }
     const float* simq = S.sim + (int64_t)qi * S.ld;
     float sv[FIN_U], rv[FIN_U];
 #pragma unroll
     for (int u = 0; u < FIN_U; ++u) {
         const int64_t d = lo + u * 32 + lane;
         sv[u] = d < hi ? simq[d] : 0.0f;
-        rv[u] = d < hi ? rk.rer[d] : 0.0f;
+        rv[u] = (MODE == 2 && d < hi) ? rk.rer[d] : 0.0f;
     }
     const uint4* hp = reinterpret_cast<const uint4*>(S.tile_hdr + ((int64_t)qi * S.tile_ld + tile) * 8);
     const uint4 h0 = hp[0], h1 = hp[1];
@@ -207,36 +176,82 @@ rerank_max_kernel(SelectArgs a, int nq, const uint64_t* __restrict__ tile_max_fi
     int n_rec = 0;
 #pragma unroll
     for (int u = 0; u < 8; ++u) n_rec += __popc(w[u]);
-    double best = -INFINITY;
-    bool any = false, nan_seen = false;
 #pragma unroll
     for (int u = 0; u < FIN_U; ++u) {
-        const bool plain = !((w[u] >> lane) & 1u) && lo + u * 32 + lane < hi;
-        if (plain) {
-            const double r = rk.blend(S.blend(c.wb_dflt, S.sim_norm(c, sv[u])), rv[u]);
-            nan_seen = nan_seen || r != r;
-            best = fmax(best, r);
-            any = true;
+        const int l = u * 32 + lane;
+        const bool plain = !((w[u] >> lane) & 1u) && lo + l < hi;
+        double f = S.blend(c.wb_dflt, S.sim_norm(c, sv[u]));
+        if (MODE == 2) f = rk.blend(f, rv[u]);
+        fn(plain, f, l);
+    }
+    for (int i0 = 0; i0 < n_rec; i0 += 32) {
+        const int i = i0 + lane;
+        const bool live = i < n_rec;
+        const double val = live ? S.rec_val[rbase + i] : 0.0;
+        const int pos = live ? (int)S.rec_pos[rbase + i] : 0;
+        double f = S.blend(__dmul_rn(S.wb, S.bm25_norm(c, val)), S.sim_norm(c, simq[lo + pos]));
+        if (MODE == 2) f = rk.blend(f, rk.rer[lo + pos]);
+        fn(live, f, pos);
+    }
+}
+
+// ---- 1b. pass 2 on the records path: tile / segment maxima of the blend R in one light pass ---------------------------
+// R = wo * final + wr * rer (webui.py:208) for every doc of the tiles that matter, from the dot score (4 B), the re-query
+// score (the shared column or the query's dense array, 4 B) and the tile's BM25 records.  A warp owns 32 consecutive
+// tiles of one query (block = 8 queries over the same tiles: the column comes through L1 once for the eight).  The PRF
+// seeds are NOT excluded here (webui.py:217 drops them from the candidates): the caller asks the segment-maximum
+// threshold for `depth` more segments instead, which keeps it a valid lower bound - at most `depth` maxima are seeds.
+// BOUND = 1 (the reference's collapsed re-query with non-negative blend weights): a.thr holds a lower bound T of the
+// k-th best R of this shard (rerank_threshold_kernel).  ONE LANE per tile forms the tile's upper bound - the blend of its
+// best COMBINED score (pass 1's tile table) with its extreme column value, every rounding monotone; a tile below T holds
+// no candidate and not the maximum of R either and costs 16 bytes.  Measured on the benchmark: 12 % of the tiles remain.
+template <int BOUND>
+__global__ void __launch_bounds__(32 * SEG_WARPS)
+rerank_max_kernel(SelectArgs a, int nq, const uint64_t* __restrict__ tile_max_fin) {
+    const FinSrc& S = a.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tb = (int64_t)blockIdx.x * 32;
+    const int qi = blockIdx.y * SEG_WARPS + warp;
+    if (qi >= nq) return;
+    const Rerank rk = a.rerank(qi);
+    const int64_t my_tile = tb + lane;
+    bool visit = my_tile < a.n_tiles;
+    if (BOUND == 1 && visit) {
+        uint64_t bound = tile_max_fin[(int64_t)qi * S.tile_ld + my_tile];
+        if (bound != KEY_EMPTY && bound < KEY_NAN) {
+            const float cx = rk.cq < 0.0f ? a.col_lo[my_tile] : a.col_hi[my_tile];
+            bound = dkey(rk.blend(dkey_inv(bound), cx));
+        }
+        visit = bound >= a.thr[qi];
+        if (!visit) a.tile_max[(int64_t)qi * S.tile_ld + my_tile] = KEY_EMPTY;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, visit);
+    uint64_t all_best = KEY_EMPTY;
+    while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t tile = tb + b;
+        double best = -INFINITY;
+        bool any = false, nan_seen = false;
+        tile_two_class<2>(a, rk, qi, tile, lane, [&](bool valid, double r, int) {
+            if (valid) {
+                nan_seen = nan_seen || r != r;
+                best = fmax(best, r);
+                any = true;
+            }
+        });
+        uint64_t key = nan_seen ? KEY_NAN : (any ? dkey(best) : KEY_EMPTY);
+        key = warp_max_u64_redux(key);
+        all_best = key > all_best ? key : all_best;
+        if (lane == 0) {
+            a.tile_max[(int64_t)qi * S.tile_ld + tile] = key;
+            if (key != KEY_EMPTY)
+                atomicMax(reinterpret_cast<unsigned long long*>(&a.seg_max[(size_t)qi * SEG_MAX + (int)(tile / a.tiles_per_seg)]),
+                          (unsigned long long)key);
         }
     }
-    for (int i = lane; i < n_rec; i += 32) {
-        const double wbb = S.rec_val[rbase + i];
-        const int pos = (int)S.rec_pos[rbase + i];
-        const double r = rk.blend(S.blend(wbb, S.sim_norm(c, simq[lo + pos])), rk.rer[lo + pos]);
-        nan_seen = nan_seen || r != r;
-        best = fmax(best, r);
-        any = true;
-    }
-    uint64_t key = nan_seen ? KEY_NAN : (any ? dkey(best) : KEY_EMPTY);
-    key = warp_max_u64_redux(key);
-    if (lane == 0) {
-        a.tile_max[(int64_t)qi * S.tile_ld + tile] = key;
-        if (key != KEY_EMPTY)
-            atomicMax(reinterpret_cast<unsigned long long*>(&a.seg_max[(size_t)qi * SEG_MAX + (int)(tile / a.tiles_per_seg)]),
-                      (unsigned long long)key);
-        if (a.max_all && key != KEY_EMPTY && key > *(volatile uint64_t*)&a.max_all[qi])
-            atomicMax(reinterpret_cast<unsigned long long*>(&a.max_all[qi]), (unsigned long long)key);
-    }
+    if (a.max_all && lane == 0 && all_best != KEY_EMPTY && all_best > *(volatile uint64_t*)&a.max_all[qi])
+        atomicMax(reinterpret_cast<unsigned long long*>(&a.max_all[qi]), (unsigned long long)all_best);
 }
 
 // ---- 2a. threshold = k-th largest segment maximum ------------------------------------------------------
@@ -391,6 +406,54 @@ collect_kernel(SelectArgs a) {
         all_best = warp_max_u64(all_best);
         if (lane == 0 && all_best != KEY_EMPTY)
             atomicMax(reinterpret_cast<unsigned long long*>(&a.max_all[qi]), (unsigned long long)all_best);
+    }
+}
+
+// the same collect on the records path (no supplied scores, no bitmaps): tile_two_class instead of the generic per-doc
+// evaluation; tile_max holds the tile's best key of THIS pass
+template <int MODE>
+__global__ void __launch_bounds__(COLLECT_THREADS)
+collect_fast_kernel(SelectArgs a) {
+    __shared__ int64_t seeds[MAX_DEPTH];
+    const int qi = blockIdx.y, lane = threadIdx.x & 31;
+    if (MODE == 2) {
+        if (threadIdx.x < MAX_DEPTH) seeds[threadIdx.x] = threadIdx.x < a.depth ? a.seeds_all[qi * MAX_DEPTH + threadIdx.x] : -1;
+        __syncthreads();
+    }
+    const uint64_t T = a.thr[qi];
+    int* cnt = a.surv_count + qi;
+    uint64_t* sk = a.surv_keys + (size_t)qi * SURV_CAP;
+    int64_t* si = a.surv_ids + (size_t)qi * SURV_CAP;
+    const uint64_t* tmax = a.tile_max + (int64_t)qi * a.S.tile_ld;
+    const Rerank rk = a.rerank(qi);
+    const int64_t warp_id = ((int64_t)blockIdx.x * COLLECT_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * COLLECT_THREADS) >> 5;
+    for (int64_t tb = warp_id * 32; tb < a.n_tiles; tb += n_warps * 32) {
+        const int64_t my_tile = tb + lane;
+        unsigned todo = __ballot_sync(0xffffffffu, my_tile < a.n_tiles && tmax[my_tile] >= T);
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t tile = tb + b, lo = tile * SEL_TILE;
+            tile_two_class<MODE>(a, rk, qi, tile, lane, [&](bool valid, double f, int l) {
+                const uint64_t key = valid ? dkey(f) : KEY_EMPTY;
+                const int64_t id = a.id_base + lo + l;
+                bool pass = valid && key >= T;
+                if (MODE == 2 && pass)
+                    for (int t = 0; t < MAX_DEPTH; ++t) pass = pass && seeds[t] != id;
+                const unsigned m = __ballot_sync(0xffffffffu, pass);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(cnt, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (pass) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < SURV_CAP) { sk[pos] = key; si[pos] = id; }
+                    }
+                }
+            });
+        }
     }
 }
 

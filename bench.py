@@ -267,7 +267,7 @@ def verify_against_oracle(eng, rows, sh_host, idf_h, df_h, avgdl, n_docs, emb, t
     n_ok = 0
     for w, j in zip(want, pick):
         got = SU.engine_outcome(ids, scores, counts, status, j)
-        assert_same_or_filter_unstable(got, w, lambda t=texts[j]: P.find_sorted(t), 1e-6, TOPN, ("verify", j, texts[j]))
+        assert_same_or_filter_unstable(got, w, lambda t=texts[j]: P.find_sorted_arrays(t), 1e-6, TOPN, ("verify", j, texts[j]))
         n_ok += 1
     return n_ok
 

@@ -77,17 +77,30 @@ FILTER_GAP_NOISE = 4e-7   # fp32 rounding of two adjacent max-normalised scores 
 def filter_alternatives(sorted_list, thresh, topn):
     """filter_searched_result (webui.py:63-80) cuts where an adjacent gap is < 1e-6.  A gap that lies
     within fp32 rounding of that threshold may legitimately fall on either side when the dot products
-    are summed in another order; return the outcomes for every threshold in thresh +- FILTER_GAP_NOISE."""
+    are summed in another order; return the outcomes for every threshold in thresh +- FILTER_GAP_NOISE.
+    `sorted_list`: list of (id, score) or an (ids, scores) pair of arrays (the >= 1 M-doc tests).  Only the first two
+    "found" gaps decide the outcome, so near-threshold gaps beyond the second CERTAIN near-tie (gap < thresh - noise)
+    cannot matter and are not enumerated - at 1 M docs nearly every gap deep in the list is near 1e-6."""
     from oracle import port
-    s = np.array([p[1] for p in sorted_list])
+    if isinstance(sorted_list, tuple):
+        ids, s = np.asarray(sorted_list[0]), np.asarray(sorted_list[1], dtype=np.float64)
+    else:
+        ids = np.array([p[0] for p in sorted_list], dtype=np.int64)
+        s = np.array([p[1] for p in sorted_list], dtype=np.float64)
     with np.errstate(invalid="ignore"):
         gaps = s[:-1] - s[1:]
-    near = np.unique(gaps[np.isfinite(gaps) & (np.abs(gaps - thresh) <= FILTER_GAP_NOISE)])
+    gaps = np.where(gaps == 0, np.inf, gaps)
+    sure = np.nonzero(gaps < thresh - FILTER_GAP_NOISE)[0]
+    limit = int(sure[1]) + 1 if len(sure) >= 2 else len(gaps)
+    region = gaps[:limit]
+    near = np.unique(region[np.isfinite(region) & (np.abs(region - thresh) <= FILTER_GAP_NOISE)])
+    if len(near) > 48:                                    # keep the enumeration bounded: the gaps closest to the threshold
+        near = near[np.argsort(np.abs(near - thresh))[:48]]
     cuts = sorted(set([thresh - FILTER_GAP_NOISE, thresh + FILTER_GAP_NOISE] + [float(g) for g in near] +
                       [float(np.nextafter(g, np.inf)) for g in near]))
     outs = []
     for t in cuts:
-        res = port.filter_searched_result(sorted_list, t)[:topn]
+        res = port.OraclePort.filter_arrays(ids, s, t, topn)
         key = [d for d, _ in res]
         if all(key != [d for d, _ in o] for o in outs):
             outs.append(res)

@@ -71,7 +71,7 @@ def main():
             n_ok = 0
             for j, text in enumerate(texts):
                 got = SU.engine_outcome(res[0], res[1], res[2], res[3], j)
-                assert_same_or_filter_unstable(got, want[j], lambda t=text: P.find_sorted(t), 1e-6, args.topn, ("nccl", j, text))
+                assert_same_or_filter_unstable(got, want[j], lambda t=text: P.find_sorted_arrays(t), 1e-6, args.topn, ("nccl", j, text))
                 n_ok += want[j][0] == "ok"
             report = {"ranks": world, "docs": args.docs, "batch": args.batch, "checked_vs_oracle": len(texts),
                       "ok_results": n_ok, "backend": dist.get_backend(), "fullsort_fallbacks": S.fullsort_fallbacks}

@@ -35,7 +35,7 @@ def _check(eng, P, texts, qs, res, topn=TOPN, what=""):
     n_ok = 0
     for j, text in enumerate(texts):
         got = SU.engine_outcome(ids, scores, counts, status, j)
-        assert_same_or_filter_unstable(got, want[j], lambda t=text: P.find_sorted(t), 1e-6, topn, (what, j, text))
+        assert_same_or_filter_unstable(got, want[j], lambda t=text: P.find_sorted_arrays(t), 1e-6, topn, (what, j, text))
         n_ok += want[j][0] == "ok"
     return n_ok
 
@@ -92,8 +92,7 @@ def test_1m_docs_topn_800_and_prf_modes(corpus):
         srt_scores = st["final"][order]
         want = capture(lambda: P.filter_arrays(order, srt_scores, 1e-6, TOPN))
         got = SU.engine_outcome(res[0], res[1], res[2], res[3], j)
-        assert_same_or_filter_unstable(got, want, lambda o=order, s=srt_scores: list(zip(o.tolist(), s)), 1e-6, TOPN,
-                                       ("1M prf off", j, text))
+        assert_same_or_filter_unstable(got, want, lambda o=order, s=srt_scores: (o, s), 1e-6, TOPN, ("1M prf off", j, text))
 
 
 def test_sharded_1m_docs_three_engines_vs_oracle():
