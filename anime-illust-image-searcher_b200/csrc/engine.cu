@@ -1117,7 +1117,8 @@ int do_finish(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys,
               const int32_t* d_witness, int topn, int64_t* out_ids, double* out_scores, int32_t* out_counts, int32_t* out_status,
               int32_t* out_amb, uint64_t* out_last_keys) {
     if (topn < 1) return fail(AIS_ERR_INVALID, "topn must be >= 1");
-    TRY(ensure_sel(e, k));
+    const int k_out = n_lists == 1 ? k : std::min<int64_t>(SEL_KMAX, (int64_t)n_lists * k);
+    TRY(ensure_sel(e, k_out));
     TRY(ensure_out(e, topn));
     ProfScope prof(e, AIS_KIND_TAIL);
     if (n_lists == 1) {
@@ -1125,8 +1126,13 @@ int do_finish(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys,
                                                    e->rest_count.as<int32_t>());
         LAUNCHED(e);
     } else {
-        TRY(merge_lists(e, d_keys, d_ids, n_lists, (int64_t)nq * k, k, k, k, nq, e->rest_keys.as<uint64_t>(),
+        TRY(merge_lists(e, d_keys, d_ids, n_lists, (int64_t)nq * k, k, k, k_out, nq, e->rest_keys.as<uint64_t>(),
                         e->rest_ids.as<int64_t>(), e->rest_count.as<int32_t>()));
+        if (k_out > k) {
+            prefix_bound_kernel<<<nq, 256, 0, e->stream>>>(d_keys, n_lists, (int64_t)nq * k, k, k, e->rest_keys.as<uint64_t>(),
+                                                          k_out, e->rest_count.as<int32_t>());
+            LAUNCHED(e);
+        }
     }
     TailParams tp;
     tp.thresh = e->p.diff_filter_thresh;
@@ -1134,7 +1140,7 @@ int do_finish(ais_engine* e, int nq, int n_lists, int k, const uint64_t* d_keys,
     tp.depth = d_max_r ? e->p.prf_depth : 0;
     tp.normalize = d_max_r ? 1 : 0;
     tp.n_total = e->total();
-    tail_kernel<<<nq, SEL_THREADS, 0, e->stream>>>(e->rest_keys.as<uint64_t>(), e->rest_ids.as<int64_t>(), k,
+    tail_kernel<<<nq, SEL_THREADS, 0, e->stream>>>(e->rest_keys.as<uint64_t>(), e->rest_ids.as<int64_t>(), k_out,
                                                   e->rest_count.as<int32_t>(), nullptr, e->top_ids.as<int64_t>(), d_max_r, tp,
                                                   d_witness, e->out_ids.as<int64_t>(), e->out_scores.as<double>(),
                                                   e->out_count.as<int32_t>(), e->out_amb.as<int32_t>(), e->last_keys.as<uint64_t>());

@@ -114,18 +114,17 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// a wait that cannot hang the GPU: a protocol error traps instead of spinning forever
+// a wait that cannot hang the GPU: a protocol error traps instead of spinning forever (~2 s of spinning; no printf
+// here - its argument buffer would put a stack frame and spills into every role of the kernel)
 __device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, int tag) {
     uint32_t spins = 0;
     long long t0 = 0;
+    (void)tag;
     while (!mbar_try_wait(bar, parity)) {
         if ((++spins & 0x3FFu) == 0) {
             const long long t = clock64();
             if (t0 == 0) t0 = t;
-            else if (t - t0 > 4000000000ll) {
-                printf("scan_tc_kernel: barrier wait timed out (role %d, block %d)\n", tag, (int)blockIdx.x);
-                __trap();
-            }
+            else if (t - t0 > 4000000000ll) __trap();
         }
     }
 }
@@ -230,12 +229,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t n_tiles = (n + TC_M - 1) / TC_M;
+    const int n_tiles = (int)((n + TC_M - 1) / TC_M);           // 32-bit tile arithmetic (n < 2^38 docs): fewer live registers
     // every CTA owns a CONTIGUOUS run of tiles: its 32 / 64 output streams sim[q][...] then advance sequentially
     // (512 B per tile and query), which the DRAM write path likes better than 148 CTAs hopping through each stream
-    const int64_t tiles_per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const int64_t tile0 = (int64_t)blockIdx.x * tiles_per_cta;
-    const int my_tiles = tile0 < n_tiles ? (int)(n_tiles - tile0 < tiles_per_cta ? n_tiles - tile0 : tiles_per_cta) : 0;
+    const int tiles_per_cta = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile0 = (int)blockIdx.x * tiles_per_cta;
+    const int my_tiles = tile0 < n_tiles ? (n_tiles - tile0 < tiles_per_cta ? n_tiles - tile0 : tiles_per_cta) : 0;
     const int total_it = my_tiles * TC_NKB;
 
     if (warp == TC_PRODUCER_WARP) {
@@ -395,7 +394,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constan
             if (warp == 0 && lane == 0) TC_TRACE(0, t, 0);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC_ACC_COLS + half * QW;
-            const int64_t row = (tile0 + t) * TC_M + quarter * 32 + lane;
+            const int64_t row = (int64_t)(tile0 + t) * TC_M + quarter * 32 + lane;
             const bool live = row < n;
             float* orow = out + row + (int64_t)(half * QW) * ld;
             if (n_chunks == 0) {                                             // nothing to read: hand the buffer back at once

@@ -188,6 +188,41 @@ merge_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ ids,
     if (threadIdx.x == 0 && out_count) out_count[qi * gridDim.x + g] = sb.count;
 }
 
+// How much of a merged list is certainly the true global order?  Every doc a shard did NOT return scores at most that
+// shard's last returned key, so merged entries strictly above the largest such key (over the lists that came back full)
+// are exact; so are the first k (the classic top-k-of-top-k argument).  The count is cut to that prefix: the filter
+// then treats the rest as unknown instead of wrong.  Shards can therefore return SHORT lists (k ~ 1024 / n_shards)
+// and the merged prefix is still ~1024 deep.
+__global__ void __launch_bounds__(256)
+prefix_bound_kernel(const uint64_t* __restrict__ keys, int n_lists, int64_t list_stride, int64_t q_stride, int k,
+                    const uint64_t* __restrict__ merged, int k_out, int32_t* __restrict__ count) {
+    __shared__ uint64_t s_bound[8];
+    __shared__ int s_cnt[8];
+    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint64_t b = KEY_EMPTY;
+    for (int l = tid; l < n_lists; l += blockDim.x) {
+        const uint64_t last = keys[(size_t)(l * list_stride + (int64_t)qi * q_stride + (k - 1))];
+        b = last > b ? last : b;
+    }
+    b = warp_max_u64(b);
+    if (lane == 0) s_bound[wid] = b;
+    __syncthreads();
+    b = s_bound[0];
+    for (int w = 1; w < 8; ++w) b = s_bound[w] > b ? s_bound[w] : b;
+    const int m = count[qi];
+    int c = 0;
+    for (int i = tid; i < m; i += blockDim.x) c += merged[(size_t)qi * k_out + i] > b;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_cnt[wid] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int exact = 0;
+        for (int w = 0; w < 8; ++w) exact += s_cnt[w];
+        const int classic = k < m ? k : m;
+        count[qi] = exact > classic ? exact : classic;
+    }
+}
+
 // ---- PRF: stored rows of the top docs, centroid, re-query vector (webui.py:195-205) ----------
 // rows_out [nq][depth][DIM]: the stored row if the doc lives on this shard, else zeros.
 __global__ void gather_top_rows_kernel(const float* __restrict__ rows, int64_t n, int64_t id_base,

@@ -84,6 +84,27 @@ class ShardedSearch:
         self.kmax = int(self.engines[0].max_select_k())
         self.fullsort_fallbacks = 0
         self.n_shards = self.comm.world * len(self.engines)
+        # stage trace (bench.py `stage_ms_per_step`): CUDA events on torch's stream at the stage boundaries, read after
+        # the step's own final synchronisation - shows where a sharded step's device time goes, gaps included
+        self.trace = False
+        self.stage_ms: dict = {}
+        self.traced_steps = 0
+        self._marks: list = []
+
+    def _mark(self, name: str) -> None:
+        if self.trace and torch.cuda.is_available():
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
+
+    def _trace_flush(self) -> None:
+        if not self._marks:
+            return
+        torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(self._marks[:-1], self._marks[1:]):
+            self.stage_ms[name] = self.stage_ms.get(name, 0.0) + a.elapsed_time(b)
+        self._marks = []
+        self.traced_steps += 1
 
     def _select_depth(self, need: int, cap: int) -> int:
         """Candidates a select stage asks for - the engine's own policy (engine.cu select_depth), from GLOBAL quantities so
@@ -94,6 +115,10 @@ class ShardedSearch:
         n_tiles = -(-per // 256)
         tps = max(1, -(-n_tiles // 2048))
         deep = (-(-n_tiles // tps)) // 2
+        # the merged list is exact down to the shards' largest last key (select.cuh prefix_bound_kernel): n_shards
+        # lists of kmax / n_shards (+ slack for an uneven split) give the same ~kmax-deep exact prefix as one engine
+        if self.n_shards > 1 and os.environ.get("AIS_SHARD_CUT", "1") != "0":
+            deep = min(deep, -(-self.kmax // self.n_shards) + 128)
         env = os.environ.get("AIS_SELECT_DEPTH")
         if env is not None and int(env) >= 0:
             deep = min(deep, int(env))
@@ -136,11 +161,14 @@ class ShardedSearch:
         depth = self.depth
         errors: list = []
         # --- pass 1: score, global maxima
+        self._mark("start")
         maxes_l = [torch.empty((nq, 2), dtype=torch.float64, device=self._dev(e)) for e in E]
         for e, m in zip(E, maxes_l):
             e.stage_score(queries, m)
+        self._mark("score")
         maxes = self.comm.all_max(self._reduce_local(maxes_l, torch.maximum))
         maxes_e = [maxes.to(self._dev(e)) for e in E]
+        self._mark("all_max(maxes)")
         prf = prf_mode != PRF_OFF and self.n_total > depth
 
         # a result longer than the selector returns: every query goes through the exact full sort (_resolve_ambiguous)
@@ -150,8 +178,12 @@ class ShardedSearch:
             keys, ids = self._cand_buffers(nq, k)
             for e, m, kk, ii in zip(E, maxes_e, keys, ids):
                 e.stage_combine(nq, m, k, kk, ii)
+            self._mark("combine+select")
             gk, gi = self._gather_lists(keys, ids)
+            self._mark("all_gather(lists)")
             res = self._finish(nq, k, gk, gi, None, topn, second_pass=False, all_ambiguous=too_long)
+            self._mark("finish")
+            self._trace_flush()
             return self._resolve_ambiguous(res, nq, topn, None, second_pass=False) + (errors,)
 
         # --- pass 1: every shard's best k1 = depth + k2 docs (the engine keeps the list: its pass-2 threshold starts from
@@ -161,7 +193,9 @@ class ShardedSearch:
         keys, ids = self._cand_buffers(nq, k1)
         for e, m, kk, ii in zip(E, maxes_e, keys, ids):
             e.stage_combine(nq, m, k1, kk, ii)
+        self._mark("combine+select")
         gk, gi = self._gather_lists([kk[:, :depth].clone() for kk in keys], [ii[:, :depth].clone() for ii in ids])
+        self._mark("all_gather(seeds)")
         host = prf_mode == PRF_CALLBACK
         rows_l = None if host else [torch.empty((nq, depth, 300), dtype=torch.float32, device=self._dev(e)) for e in E]
         top = None
@@ -170,6 +204,7 @@ class ShardedSearch:
                             None if host else rows_l[j])
             if j == 0:
                 top = r
+        self._mark("top rows")
         q2 = None
         rows_e = [None] * len(E)
         if host:
@@ -202,6 +237,7 @@ class ShardedSearch:
         else:
             rows = self.comm.all_sum(self._reduce_local(rows_l, torch.add))
             rows_e = [rows.to(self._dev(e)) for e in E]
+        self._mark("all_sum(rows)")
 
         # --- pass 2
         k = k2
@@ -209,9 +245,13 @@ class ShardedSearch:
         maxr_l = [torch.empty((nq,), dtype=torch.float64, device=self._dev(e)) for e in E]
         for e, r, mr, kk, ii in zip(E, rows_e, maxr_l, keys, ids):
             e.stage_requery(nq, q2, r, prf_mode, k, mr, kk, ii)
+        self._mark("requery+select")
         maxr = self.comm.all_max(self._reduce_local(maxr_l, torch.maximum))
         gk, gi = self._gather_lists(keys, ids)
+        self._mark("all_max(maxr)+all_gather(lists)")
         res = self._finish(nq, k, gk, gi, maxr, topn, second_pass=True, all_ambiguous=too_long)
+        self._mark("finish")
+        self._trace_flush()
         return self._resolve_ambiguous(res, nq, topn, maxr, second_pass=True) + (errors,)
 
     def _finish(self, nq: int, k: int, gk, gi, maxr, topn: int, second_pass: bool, all_ambiguous: bool = False):

@@ -290,6 +290,8 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1..4096 (extra key batch_sweep): SIMT -> mma.sync -> tcgen05 crossover")
     ap.add_argument("--verify", type=int, default=4, help="queries of a timed batch re-checked against the oracle on a host copy of "
                                                           "the benchmarked index (0 = off; 1 GPU only)")
+    ap.add_argument("--dump-results", default="", help="write the ids / scores / counts of every timed step to this .npz "
+                                                       "(rank 0): lets runs at different --gpus be diffed query by query")
     ap.add_argument("--prf", default="stored_rows", choices=["stored_rows", "full"],
                     help="stored_rows: the reference's re-query (collapsed centroid [c,0,...,0]: served by the one-sector-per-doc "
                          "column scan); full: the un-collapsed centroid (a second dense pass over the rows)")
@@ -416,6 +418,10 @@ def main():
     sampler.mark_end()
     st = eng.stats()
     eng.set_profiling(False)
+    if args.dump_results and rank == 0:
+        import numpy as np
+        np.savez_compressed(args.dump_results, ids=np.stack([d[1] for d in done]), scores=np.stack([d[2] for d in done]),
+                            counts=np.stack([d[3] for d in done]), status=np.stack([d[4] for d in done]))
 
     n_queries = args.steps * b
     value = n_queries / (dev_ms * 1e-3)
@@ -492,6 +498,36 @@ def main():
             except Exception as exc:   # noqa: BLE001
                 parity = {"checked": 0, "ok": None, "error": "verification could not run: %r" % (exc,)}
         host_copy = None
+
+    # ---- where a sharded step's device time goes (events at the stage boundaries, a separate untimed run) and what part
+    # of a step does not shrink with the shard (the same batch over an index of 8 192 docs per GPU)
+    stage_ms = None
+    if S is not None:
+        S.trace = True
+        run_steps(max(2, args.steps // 2), b, args.warmup)
+        S.trace = False
+        stage_ms = {k: v / max(1, S.traced_steps) for k, v in S.stage_ms.items()}
+    fixed = None
+    if not args.no_modes:
+        try:
+            n_small = 8192 * world
+            e0 = stage(n_small, min(256, b))[0]
+            e0.use_torch_stream()
+            S0 = shard.ShardedSearch([e0], n_small) if world > 1 else None
+            f0 = make_search(e0, S0)
+            run_steps(3, b, 0, fn=f0)
+            ms0 = run_steps(args.steps, b, 3, fn=f0)[0]
+            e0.set_profiling(True); e0.reset_stats()
+            run_steps(args.steps, b, 3, fn=f0)
+            s0 = e0.stats(); e0.set_profiling(False)
+            fixed = {"ms_per_step": ms0 / args.steps, "docs": n_small,
+                     "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in s0["kernels"].items() if v["brackets"]},
+                     "launches_per_step": s0["kernel_launches"] / args.steps,
+                     "what": "the same batches over an index of 8192 docs per GPU: launches, collectives, merges, host work - "
+                             "everything that does not shrink with the shard"}
+            e0.close()
+        except Exception as exc:   # noqa: BLE001
+            fixed = {"error": repr(exc)}
 
     sweep = None
     other_configs = None
@@ -589,7 +625,10 @@ def main():
             "bound_passes": int(st["bound_passes"]), "tiles_per_seg": int(st["tiles_per_seg"]),
             "device_bytes": int(st["bytes_device"]),
             "index_build_s": t_build,
+            "fixed_ms_per_step": fixed,
         }
+        if stage_ms:
+            line["stage_ms_per_step"] = stage_ms
         if sweep:
             line["batch_sweep" if args.sweep else "other_batch_sizes"] = sweep
         if other_configs:

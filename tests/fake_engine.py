@@ -172,7 +172,12 @@ class FakeStageEngine:
         last = np.zeros(nq, dtype=np.uint64)
         wit = None if witness is None else self._np(witness)
         for i in range(nq):
-            rk, ri, m = top_sorted(kk[:, i].ravel(), ii[:, i].ravel(), k)
+            # engine.cu do_finish: merged list up to SEL_KMAX deep, cut to its certainly-exact prefix (prefix_bound_kernel)
+            k_out = k if n_lists == 1 else min(1024, n_lists * k)
+            rk, ri, m = top_sorted(kk[:, i].ravel(), ii[:, i].ravel(), k_out)
+            if k_out > k:
+                bound = kk[:, i, k - 1].max()
+                m = max(min(k, m), int((rk[:m] > bound).sum()))
             vals = dkey_inv(rk[:m])
             if max_r is not None and self._np(max_r)[i] > 0:
                 vals = vals / self._np(max_r)[i]
