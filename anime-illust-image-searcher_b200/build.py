@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libais_b200.so")
 SOURCES = ["engine.cu", "pickle_csr.cpp"]
-HEADERS = ["common.cuh", "finals.cuh", "scan.cuh", "scan_tc.cuh", "bm25.cuh", "build.cuh", "select2.cuh", "select.cuh", os.path.join("..", "..", "include", "ais_b200.h")]
+HEADERS = ["common.cuh", "finals.cuh", "scan.cuh", "scan_tc.cuh", "scan_pair.cuh", "bm25.cuh", "build.cuh", "select2.cuh", "select.cuh", os.path.join("..", "..", "include", "ais_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared", "-Xptxas", "-v"]
 

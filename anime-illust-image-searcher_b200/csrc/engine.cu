@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include "scan_tc.cuh"
+#include "scan_pair.cuh"
 #include "select.cuh"
 #include "select2.cuh"
 
@@ -211,7 +212,8 @@ struct ais_engine {
     bool tc_wide = true;       // > 32 queries left: 64 queries per tcgen05 pass (AIS_SCAN_TC_WIDE=0: 32)
     int tc_min = 9;            // >= tc_min queries left in a batch: tcgen05 scan, 32 or 64 queries per pass (AIS_SCAN_TC_MIN; 0 = off)
     Buf qsplit;                // [64][300] hi | lo images of the queries of one tcgen05 pass
-    CUtensorMap tm_rows, tm_q[2];       // tm_q[0]: 32 queries per pass, tm_q[1]: 64
+    CUtensorMap tm_rows, tm_q[3];       // tm_q[0]: 32 queries per pass, tm_q[1]: 64, tm_q[2]: 64 in boxes of 32 rows (CTA pair)
+    int scan_pair = 9;                  // AIS_SCAN_PAIR: ring depth (8 / 9) of scan_pair_kernel; 0 = single-CTA scan_tc_kernel<64>
     const void* tm_rows_ptr = nullptr;  int64_t tm_rows_n = -1;  const void* tm_q_ptr = nullptr;
     double kind_ms[AIS_N_KINDS] = {0};          // summed CUDA-event time per kernel class (profiling on)
     int64_t kind_launches[AIS_N_KINDS] = {0};
@@ -497,6 +499,7 @@ int launch_scan_tc(ais_engine* e, const float* d_q, int nq, bool wide, float* ou
     if (e->tm_q_ptr != e->qsplit.p) {
         TRY(make_row_tmap(&e->tm_q[0], e->qsplit.p, 2 * 32, 32));
         TRY(make_row_tmap(&e->tm_q[1], e->qsplit.p, 2 * 64, 64));
+        TRY(make_row_tmap(&e->tm_q[2], e->qsplit.p, 2 * 64, TCP_NH));
         e->tm_q_ptr = e->qsplit.p;
     }
     if (e->tm_rows_ptr != e->rows.p || e->tm_rows_n != e->n_vec) {
@@ -509,7 +512,15 @@ int launch_scan_tc(ais_engine* e, const float* d_q, int nq, bool wide, float* ou
     const int64_t n_tiles = (e->n_vec + TC_M - 1) / TC_M;
     const int grid = (int)(n_tiles < e->sm_count ? n_tiles : e->sm_count);
     ProfScope prof(e, AIS_KIND_SCAN);
-    if (wide) launch_tc_variant<64, 2, 1, 4, 2, 1, 2>(e, grid, out, max_keys, nq);
+    if (wide && e->scan_pair > 0 && e->sm_count >= 2) {
+        // CTA pairs: half of the query images per SM, a ring of 8 / 9 landing stages (scan_pair.cuh)
+        const int64_t n_steps = (n_tiles + 1) / 2;
+        const int pairs = (int)(n_steps < e->sm_count / 2 ? n_steps : e->sm_count / 2);
+        if (e->scan_pair >= 9)
+            scan_pair_kernel<9><<<2 * pairs, TC_THREADS, tcp_smem_bytes(9), e->stream>>>(e->tm_rows, e->tm_q[2], e->n_vec, out, e->ld, max_keys, nq);
+        else
+            scan_pair_kernel<8><<<2 * pairs, TC_THREADS, tcp_smem_bytes(8), e->stream>>>(e->tm_rows, e->tm_q[2], e->n_vec, out, e->ld, max_keys, nq);
+    } else if (wide) launch_tc_variant<64, 2, 1, 4, 2, 1, 2>(e, grid, out, max_keys, nq);
     else launch_tc_variant<32, 3, 1, 6, 4, 1, 2>(e, grid, out, max_keys, nq);
     LAUNCHED(e);
     e->scan_launches++;
@@ -589,6 +600,8 @@ int set_scan_attrs() {
     CK(cudaFuncSetAttribute(scan_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_mma_smem_bytes<16>()));
     CK(cudaFuncSetAttribute(scan_tc_kernel<32, 3, 1, 6, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(32, 6)));
     CK(cudaFuncSetAttribute(scan_tc_kernel<64, 2, 1, 4, 2, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(64, 4)));
+    CK(cudaFuncSetAttribute(scan_pair_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp_smem_bytes(8)));
+    CK(cudaFuncSetAttribute(scan_pair_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp_smem_bytes(9)));
     CK(cudaFuncSetAttribute(sort_survivors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SURV_CAP * 16));
     return AIS_OK;
 }
@@ -1448,6 +1461,7 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
     e->use_mma = !(simt && simt[0] == '1');
     if (const char* tcm = getenv("AIS_SCAN_TC_MIN")) e->tc_min = atoi(tcm);
     if (const char* tcw = getenv("AIS_SCAN_TC_WIDE")) e->tc_wide = atoi(tcw) != 0;
+    if (const char* sp = getenv("AIS_SCAN_PAIR")) e->scan_pair = atoi(sp);
     if (const char* rd = getenv("AIS_REQUERY_DENSE")) e->requery_dense = atoi(rd) != 0;
     if (const char* nb = getenv("AIS_TILE_BOUND")) e->no_bound = atoi(nb) == 0;
     if (const char* ns = getenv("AIS_NO_TILE_SKIP")) e->no_skip = atoi(ns) != 0;

@@ -140,7 +140,10 @@ __device__ __forceinline__ bool elect_one() {
 // a_full seen, issued), 2 split warp 4 (per iteration: full_raw seen, computed, a_empty seen, arrived), 3 producer.
 #ifdef AIS_TC_TRACE
 __device__ long long g_tc_trace[4][256][4];
-#define TC_TRACE(role, idx, slot) do { if (blockIdx.x == 0 && (idx) < 256) g_tc_trace[role][idx][slot] = clock64(); } while (0)
+#ifndef AIS_TC_TRACE_BLOCK
+#define AIS_TC_TRACE_BLOCK 0
+#endif
+#define TC_TRACE(role, idx, slot) do { if (blockIdx.x == AIS_TC_TRACE_BLOCK && (idx) < 256) g_tc_trace[role][idx][slot] = clock64(); } while (0)
 #else
 #define TC_TRACE(role, idx, slot) do { } while (0)
 #endif
@@ -167,8 +170,14 @@ __global__ void split_queries_kernel(const float* __restrict__ q, int nq, int n_
 //           6 x 16 KB ring: 2.10 ms per pass = 12.0 GB read + 1.28 GB written at 6.3 TB/s (0.97 of the copy peak).
 //   N = 64: <64,2,1,4,2,2>: 3 accumulators x 64 columns x 2 buffers = 384 columns + 2 A stages; 160 KB of queries,
 //           4 x 16 KB ring: 2.67 ms per pass (5.45 TB/s of total traffic).
-// What did NOT matter (each tried): ring depth 4/6/9, 2 vs 4 vs 5 A stages, rotating vs K-range accumulators, one vs
-// two accumulator buffers at equal instruction count.  What did: the MMA issue sequence (unrolled, uniform registers:
+// What did NOT matter (each tried): ring depth 4/6/9 at N = 32, 2 vs 4 vs 5 A stages, rotating vs K-range accumulators,
+// one vs two accumulator buffers at equal instruction count.  At N = 64 (round 2, 10 M docs): <64,1,1,4,4,1,2> (one main
+// accumulator, FOUR A stages) 2.654 ms vs 2.676 ms for <64,2,1,4,2,1,2>, <64,2,1,4,4,2,2> (half-k-block A stages)
+// 2.94 ms - so the A hand-over is not what holds the 64-query kernel at 0.69 of the copy peak.  The CTA timeline
+// (profiles/r01_d_scan_tc64_cta_timeline.txt) shows the split warps waiting 800-1400 clocks for full_raw: 4 x 16 KB per
+// SM in flight is too little at the loaded HBM latency (~1.8 us); the 160 KB of query images leave no room for more.
+// Halving the query images per SM (tcgen05 cta_group::2: each CTA of a pair holds 32 of the 64 query rows) is the
+// open route to a 8-9 stage ring.  What did: the MMA issue sequence (unrolled, uniform registers:
 // 3.8 -> 2.2 ms) and the instruction count of the split and epilogue warps, which share four issue slots.
 template <int TC_N, int TC_MAIN, int TC_CROSS, int TC_RAW_STAGES, int TC_A_STAGES, int TC_A_SUB, int TC_NBUF>
 __global__ void __launch_bounds__(TC_THREADS, 1)

@@ -47,6 +47,8 @@ def scan_kernel_for(batch: int):
     """(kernel name, key into profiles/traffic.json, queries per pass) of the scan launch that dominates a batch of this size"""
     left = min(batch, 256)
     if left >= 33:
+        if os.environ.get("AIS_SCAN_PAIR", "9") != "0":
+            return "scan_pair_kernel<9> (tcgen05 cta_group::2 kind::tf32 3xTF32, CTA pairs, 64 queries per pass)", "scan_pair64", 64
         return "scan_tc_kernel<64> (tcgen05 kind::tf32 3xTF32, 64 queries per pass)", "scan_tc64", 64
     if left >= 9:
         return "scan_tc_kernel<32> (tcgen05 kind::tf32 3xTF32, 32 queries per pass)", "scan_tc32", 32

@@ -28,17 +28,18 @@ B.lib.ais_debug_tc_trace.restype = C.c_int
 B.lib.ais_debug_tc_trace.argtypes = [C.c_void_p, C.c_void_p]
 B.check(B.lib.ais_debug_tc_trace(eng._h, out.ctypes.data))
 t0 = out[3, 0, 0]
+print('t0', t0)
 ep = out[0, :60, :3] - t0
 print("epilogue per tile: [acc_full seen, released, stores done] and deltas; tile period")
-for t in range(2, 20):
+for t in range(2, 16):
     print(t, ep[t], "wait->release %d, release->done %d, period %d" % (ep[t,1]-ep[t,0], ep[t,2]-ep[t,1], ep[t,0]-ep[t-1,0]))
 mm = out[1, :256, :2] - t0
 print("MMA per A stage: [a_full seen, issued]; period")
-for i in range(40, 70):
+for i in range(40, 90):
     print(i, mm[i], "issue %d period %d" % (mm[i,1]-mm[i,0], mm[i,0]-mm[i-1,0]))
 sp = out[2, :128, :4] - t0
 print("split warp 4 per own iteration: [full_raw seen, computed, a_empty seen, arrived]")
-for i in range(20, 40):
+for i in range(15, 45):
     print(i, sp[i], "compute %d, wait a_empty %d, st+arrive %d, period %d" % (sp[i,1]-sp[i,0], sp[i,2]-sp[i,1], sp[i,3]-sp[i,2], sp[i,0]-sp[i-1,0]))
 pr = out[3, :256, 0] - t0
 print("producer issue times (deltas):", np.diff(pr[40:80]))
