@@ -231,8 +231,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_query * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
-        "config": {"workload": workload_text(args.docs, 1, 1), "docs": args.docs, "batch": 1, "topn": TOPN,
-                   "sample": "a timed step = one query on a %d-doc index of the same generator family (ms_per_step); "
+        "config": {"workload": workload_text(args.docs, max(1, args.gpus), args.batch), "docs": args.docs, "batch": args.batch, "topn": TOPN,
+                   "prf": args.prf,
+                   "sample": "the reference scores one query at a time (no batching, webui.py:345-390): a timed step = one query on a %d-doc index of the same generator family (ms_per_step); "
                              "value = O(N) extrapolation of the %d-doc measurement to %d docs"
                              % (main["docs"], largest["docs"], args.docs)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(lt), "kind": largest["kind"],
