@@ -122,6 +122,23 @@ struct Bm25Args {
 // rec_base[q] + tile_off[q][tile] of the record pools.  tile_off = the number of postings of the query's terms that lie
 // BEFORE the tile (read off the slice table): a tile has at most as many records as postings, so the regions never
 // overlap and no cursor is shared (a per-query atomic cursor serialised ~10 M atomics per batch on 256 addresses).
+// One-off check at load time: every posting names a doc of the shard and the doc ids of a term ascend strictly
+// - what the tile slices (binary search) and the per-tile accumulators (acc[doc - lo]) rely on.  One warp per term.
+__global__ void validate_postings_kernel(const int64_t* __restrict__ post_ptr, const int32_t* __restrict__ post_doc, int n_vocab,
+                                         int64_t n_docs, int* __restrict__ bad_term) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_vocab; t += warps) {
+        const int64_t a = post_ptr[t], b = post_ptr[t + 1];
+        bool bad = false;
+        for (int64_t p = a + lane; p < b; p += 32) {
+            const int32_t d = post_doc[p];
+            bad = bad || d < 0 || d >= n_docs || (p > a && post_doc[p - 1] >= d);
+        }
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMax(bad_term, t + 1);
+    }
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(BM25_THREADS, MINB)
 bm25_score_kernel(Bm25Args A) {

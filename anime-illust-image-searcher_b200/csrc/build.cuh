@@ -17,11 +17,14 @@ namespace ais {
 
 constexpr int BUILD_THREADS = 256;
 constexpr int BUILD_PAIRS = 2048;            // (term, doc) pairs sorted per chunk
-constexpr int BUILD_MAX_DOC_TAGS = 256;      // longest supported tag list of one doc (the tagger emits ~30)
+constexpr int BUILD_MAX_DOC_TAGS = BUILD_PAIRS;   // longest tag list of one doc: a doc never spans sort chunks (the tagger emits ~30;
+                                                  // round 1 stopped at 256 - the per-warp scratch lists are gone)
 
-// distinct terms of one doc with their multiplicities, by one warp.  out_* need room for len entries.
-// Returns the number of distinct terms (same on all lanes).  Order: first occurrence (like the dict of genmodel.py:64-66).
-__device__ inline int warp_dedupe(const int32_t* __restrict__ ids, int len, int32_t* out_term, int32_t* out_tf) {
+// Distinct terms of one doc with their multiplicities, by one warp, 32 tokens at a time.  emit(term, tf, first, mask) is
+// called by ALL lanes for every group of 32 tokens: `first` = this lane's token is the first occurrence of its term in
+// the doc (genmodel.py:64-66 counts into a dict), `mask` = ballot of `first`.  Returns the number of distinct terms.
+template <class F>
+__device__ inline int warp_distinct(const int32_t* __restrict__ ids, int len, F emit) {
     const int lane = threadIdx.x & 31;
     int n_out = 0;
     for (int base = 0; base < len; base += 32) {
@@ -36,11 +39,7 @@ __device__ inline int warp_dedupe(const int32_t* __restrict__ ids, int len, int3
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, first);
-        if (first) {
-            const int pos = n_out + __popc(m & ((1u << lane) - 1u));
-            out_term[pos] = t;
-            out_tf[pos] = tf;
-        }
+        emit(t, tf, first, m);
         n_out += __popc(m);
     }
     return n_out;
@@ -50,25 +49,21 @@ __device__ inline int warp_dedupe(const int32_t* __restrict__ ids, int len, int3
 __global__ void __launch_bounds__(BUILD_THREADS)
 build_count_kernel(const int64_t* __restrict__ seq_ptr, const int32_t* __restrict__ seq_ids, int64_t n_docs, int64_t docs_per_cta,
                    int32_t n_terms, int32_t* __restrict__ count, int64_t* __restrict__ doc_len, int* __restrict__ error) {
-    __shared__ int32_t s_term[BUILD_THREADS / 32][BUILD_MAX_DOC_TAGS];
-    __shared__ int32_t s_tf[BUILD_THREADS / 32][BUILD_MAX_DOC_TAGS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t lo = (int64_t)blockIdx.x * docs_per_cta;
     const int64_t hi = lo + docs_per_cta < n_docs ? lo + docs_per_cta : n_docs;
     int32_t* row = count + (size_t)blockIdx.x * n_terms;
     for (int64_t d = lo + warp; d < hi; d += BUILD_THREADS / 32) {
         const int64_t a = seq_ptr[d];
-        const int len = (int)(seq_ptr[d + 1] - a);
-        if (lane == 0) doc_len[d] = len;                               // genmodel.py:69
-        if (len > BUILD_MAX_DOC_TAGS) { if (lane == 0) atomicExch(error, 1); continue; }
-        const int nu = warp_dedupe(seq_ids + a, len, s_term[warp], s_tf[warp]);
-        __syncwarp();
-        for (int i = lane; i < nu; i += 32) {
-            const int32_t t = s_term[warp][i];
-            if (t < 0 || t >= n_terms) atomicExch(error, 2);
-            else atomicAdd(&row[t], 1);                                  // genmodel.py:72-73
-        }
-        __syncwarp();
+        const int64_t len64 = seq_ptr[d + 1] - a;
+        if (lane == 0) doc_len[d] = len64;                             // genmodel.py:69
+        if (len64 < 0 || len64 > BUILD_MAX_DOC_TAGS) { if (lane == 0) atomicExch(error, 1); continue; }
+        warp_distinct(seq_ids + a, (int)len64, [&](int32_t t, int, bool first, unsigned) {
+            if (first) {
+                if (t < 0 || t >= n_terms) atomicExch(error, 2);
+                else atomicAdd(&row[t], 1);                              // genmodel.py:72-73
+            }
+        });
     }
 }
 
@@ -91,8 +86,6 @@ build_fill_kernel(const int64_t* __restrict__ seq_ptr, const int32_t* __restrict
                   const int64_t* __restrict__ post_ptr, int32_t* __restrict__ post_doc, int32_t* __restrict__ post_tf) {
     __shared__ uint64_t key[BUILD_PAIRS];          // term << 32 | doc (global id < 2^31)
     __shared__ int32_t val[BUILD_PAIRS];           // tf
-    __shared__ int32_t s_term[BUILD_THREADS / 32][BUILD_MAX_DOC_TAGS];
-    __shared__ int32_t s_tf[BUILD_THREADS / 32][BUILD_MAX_DOC_TAGS];
     __shared__ int s_n;
     __shared__ int64_t s_next;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -120,17 +113,18 @@ build_fill_kernel(const int64_t* __restrict__ seq_ptr, const int32_t* __restrict
         for (int64_t d = d0 + warp; d < d1; d += BUILD_THREADS / 32) {
             const int64_t a = seq_ptr[d];
             const int len = (int)(seq_ptr[d + 1] - a);
-            // docs longer than the per-warp scratch were rejected by build_count_kernel's error flag
-            const int nu = warp_dedupe(seq_ids + a, len, s_term[warp], s_tf[warp]);
-            __syncwarp();
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_n, nu);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (int i = lane; i < nu; i += 32) {
-                key[base + i] = ((uint64_t)(uint32_t)s_term[warp][i] << 32) | (uint64_t)(uint32_t)d;
-                val[base + i] = s_tf[warp][i];
-            }
-            __syncwarp();
+            // docs longer than a sort chunk were rejected by build_count_kernel's error flag; the order of the pairs inside
+            // the chunk is irrelevant (sorted by (term, doc) below), so every group of 32 tokens reserves its own slots
+            warp_distinct(seq_ids + a, len, [&](int32_t t, int tf, bool first, unsigned m) {
+                int base = 0;
+                if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (first) {
+                    const int slot = base + __popc(m & ((1u << lane) - 1u));
+                    key[slot] = ((uint64_t)(uint32_t)t << 32) | (uint64_t)(uint32_t)d;
+                    val[slot] = tf;
+                }
+            });
         }
         __syncthreads();
         const int np = s_n;

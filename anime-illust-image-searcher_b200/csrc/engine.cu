@@ -1609,6 +1609,20 @@ int ais_load_bm25(ais_engine* e, const int64_t* post_ptr, const int32_t* post_do
                                                                           e->g1.as<double>());
         LAUNCHED(e);
     }
+    if (n_post > 0 && n_terms > 0) {                      // the kernels index per-tile arrays with these ids: check them once
+        TRY(dev_alloc(e, e->scratch64, sizeof(double)));
+        CK(cudaMemsetAsync(e->scratch64.p, 0, sizeof(int), e->stream));
+        validate_postings_kernel<<<4 * e->sm_count, 256, 0, e->stream>>>(e->post_ptr.as<int64_t>(), e->post_doc.as<int32_t>(), n_terms,
+                                                                        n_docs, e->scratch64.as<int>());
+        LAUNCHED(e);
+        int bad_term = 0;
+        CK(cudaMemcpyAsync(&bad_term, e->scratch64.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (bad_term > 0) {
+            e->n_vocab = 0; e->n_bm25 = 0; e->n_post = 0;
+            return fail(AIS_ERR_INVALID, "posting list of term %d: doc ids must lie in [0, n_docs) and ascend strictly", bad_term - 1);
+        }
+    }
     CK(cudaStreamSynchronize(e->stream));
     e->avgdl = avgdl;
     e->n_vocab = n_terms;
@@ -1659,7 +1673,7 @@ int ais_build_bm25(ais_engine* e, const int64_t* seq_ptr, const int32_t* seq_ids
         CK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaMemcpyAsync(&n_post, (const char*)e->post_ptr.p + (size_t)n_terms * sizeof(int64_t), sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
-        if (err == 1) return fail(AIS_ERR_UNSUPPORTED, "a doc has more than %d tags", BUILD_MAX_DOC_TAGS);
+        if (err == 1) return fail(AIS_ERR_UNSUPPORTED, "a doc has more than %d tags (one sort chunk of the builder)", BUILD_MAX_DOC_TAGS);
         if (err == 2) return fail(AIS_ERR_INVALID, "term id outside [0, %d)", n_terms);
         TRY(dev_alloc(e, e->post_doc, (size_t)n_post * sizeof(int32_t)));
         TRY(dev_alloc(e, e->post_tf, (size_t)n_post * sizeof(int32_t)));

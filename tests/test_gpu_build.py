@@ -93,4 +93,30 @@ def test_build_rejects_bad_input():
     with pytest.raises(AisError):
         eng.build_bm25(np.array([0, 2], np.int64), np.array([0, 99], np.int32), 10)      # term id out of range
     with pytest.raises(AisError):
-        eng.build_bm25(np.array([0, 300], np.int64), np.arange(300, dtype=np.int32), 400)  # more than 256 tags in a doc
+        eng.build_bm25(np.array([0, 2049], np.int64), np.arange(2049, dtype=np.int32) % 400, 400)  # longer than a sort chunk
+
+
+def test_build_docs_with_long_tag_lists():
+    """no 256-tags cap.  Docs of 300 / 1500 / 2048 tokens (with repeats) next to ordinary ones: doc lengths,
+    document frequencies and the (term, doc, tf) postings equal the dict-based transposition of genmodel.py:64-73."""
+    rng = np.random.default_rng(77)
+    V = 900
+    lens = [30, 300, 12, 1500, 2048, 0, 45, 257, 31]
+    seqs = [rng.integers(0, V, size=n).astype(np.int32) for n in lens]
+    ptr = np.cumsum([0] + lens).astype(np.int64)
+    ids = np.concatenate(seqs)
+    eng = E.SearchEngine()
+    doc_len, avgdl, idf, df = G.build_index(eng, ptr, ids, V)
+    assert doc_len.tolist() == lens
+    want = {}
+    for d, s in enumerate(seqs):
+        terms, tfs = np.unique(s, return_counts=True)
+        for t, f in zip(terms.tolist(), tfs.tolist()):
+            want[(t, d)] = f
+    pp, pd, pt = eng.export_postings()
+    terms = np.repeat(np.arange(V), np.diff(pp))
+    got = {(t, d): f for t, d, f in zip(terms.tolist(), pd.tolist(), pt.tolist())}
+    assert got == want
+    assert np.array_equal(df, np.bincount([t for t, _ in want], minlength=V))
+    for t in range(V):
+        assert np.all(np.diff(pd[pp[t]: pp[t + 1]]) > 0)

@@ -498,3 +498,23 @@ def test_clustered_top_docs_overflow_the_streaming_select():
             else:
                 want = capture(P.rerank, f, topn)
             assert_same(capture(webui_api.get_doc2vec_based_reranked_scores, f, topn), want, (mode, topn))
+
+
+def test_load_rejects_corrupt_posting_lists():
+    """ais_load_bm25 validates what the kernels index with - doc ids inside the shard and strictly ascending per
+    term (one device pass at load time); a corrupt index is an error, not an out-of-bounds write."""
+    from ais_b200 import binding as B
+    eng = E.SearchEngine(device=0, max_batch=1)
+    n_docs, n_terms = 1000, 3
+    idf = np.ones(n_terms)
+    doc_len = np.full(n_docs, 2, dtype=np.int64)
+    ptr = np.array([0, 3, 5, 6], dtype=np.int64)
+    good = np.array([1, 5, 999, 0, 7, 42], dtype=np.int32)
+    eng.load_bm25(ptr, good, None, idf, doc_len, 2.0)
+    for bad, term in ((np.array([1, 5, 1000, 0, 7, 42], np.int32), 0),        # beyond the shard
+                      (np.array([1, 5, 999, 7, 7, 42], np.int32), 1),         # not strictly ascending
+                      (np.array([1, 5, 999, 0, 7, -1], np.int32), 2)):        # negative
+        with pytest.raises(B.AisError) as ei:
+            eng.load_bm25(ptr, bad, None, idf, doc_len, 2.0)
+        assert "term %d" % term in str(ei.value)
+    eng.close()
