@@ -42,6 +42,7 @@ class AisStats(C.Structure):
         ("fullsort_fallbacks", C.c_int64), ("bytes_device", C.c_int64), ("column_scan_launches", C.c_int64),
         ("tiles_per_seg", C.c_int64),
         ("kind_ms", C.c_double * 8), ("kind_launches", C.c_int64 * 8), ("bound_passes", C.c_int64), ("bitmap_batches", C.c_int64),
+        ("pair_scan_launches", C.c_int64),
     ]
 
 

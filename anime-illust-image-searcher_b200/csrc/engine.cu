@@ -197,7 +197,7 @@ struct ais_engine {
     int h_out_cap = 0;
 
     // stats
-    int64_t column_scan_launches = 0, last_tiles_per_seg = 0, bound_passes = 0;
+    int64_t column_scan_launches = 0, last_tiles_per_seg = 0, bound_passes = 0, pair_scan_launches = 0;
     Buf colbuf;                    // rows[.][col_comp] as a compact array (column mode of the PRF re-query)
     int col_comp = -1;  const void* col_rows_ptr = nullptr;  int64_t col_n = -1;
     bool rer_column = false;       // current batch: rer[q][d] = colbuf[d] * d_q2[q][col_comp], never materialised
@@ -520,6 +520,7 @@ int launch_scan_tc(ais_engine* e, const float* d_q, int nq, bool wide, float* ou
             scan_pair_kernel<9><<<2 * pairs, TC_THREADS, tcp_smem_bytes(9), e->stream>>>(e->tm_rows, e->tm_q[2], e->n_vec, out, e->ld, max_keys, nq);
         else
             scan_pair_kernel<8><<<2 * pairs, TC_THREADS, tcp_smem_bytes(8), e->stream>>>(e->tm_rows, e->tm_q[2], e->n_vec, out, e->ld, max_keys, nq);
+        e->pair_scan_launches++;
     } else if (wide) launch_tc_variant<64, 2, 1, 4, 2, 1, 2>(e, grid, out, max_keys, nq);
     else launch_tc_variant<32, 3, 1, 6, 4, 1, 2>(e, grid, out, max_keys, nq);
     LAUNCHED(e);
@@ -1475,6 +1476,23 @@ int ais_create(ais_engine** out, int device_id, const ais_params* p) {
 
     int s = set_scan_attrs();
     if (s != AIS_OK) { cudaStreamDestroy(e->own_stream); delete e; return s; }
+    if (e->scan_pair > 0) {
+        // the CTA-pair scan needs two SMs of one TPC per cluster: ask the runtime whether such clusters can be resident at
+        // all (MIG slices, odd SM counts); otherwise the single-CTA kernel serves the 64-query passes
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2, 1, 1);
+        cfg.blockDim = dim3(TC_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = e->scan_pair >= 9 ? tcp_smem_bytes(9) : tcp_smem_bytes(8);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        const cudaError_t ce = e->scan_pair >= 9 ? cudaOccupancyMaxActiveClusters(&n_clusters, scan_pair_kernel<9>, &cfg)
+                                                  : cudaOccupancyMaxActiveClusters(&n_clusters, scan_pair_kernel<8>, &cfg);
+        if (ce != cudaSuccess || n_clusters < 1) { (void)cudaGetLastError(); e->scan_pair = 0; }
+    }
     *out = e;
     return AIS_OK;
 }
@@ -2006,6 +2024,7 @@ int ais_get_stats(ais_engine* e, ais_stats* out) {
     out->bytes_device = e->bytes_device;
     out->column_scan_launches = e->column_scan_launches;
     out->tiles_per_seg = e->last_tiles_per_seg;
+    out->pair_scan_launches = e->pair_scan_launches;
     out->bound_passes = e->bound_passes + e->skip_passes;
     out->bitmap_batches = e->bitmap_batches;
     return AIS_OK;
@@ -2014,7 +2033,7 @@ int ais_reset_stats(ais_engine* e) {
     if (!e) return fail(AIS_ERR_INVALID, "NULL engine");
     DeviceGuard g(e->device);
     TRY(drain_events(e));
-    e->scan_launches = e->kernel_launches = e->fullsort_fallbacks = e->column_scan_launches = e->bound_passes = e->bitmap_batches = e->skip_passes = 0;
+    e->scan_launches = e->kernel_launches = e->fullsort_fallbacks = e->column_scan_launches = e->bound_passes = e->bitmap_batches = e->skip_passes = e->pair_scan_launches = 0;
     for (int k = 0; k < AIS_N_KINDS; ++k) { e->kind_ms[k] = 0.0; e->kind_launches[k] = 0; }
     return AIS_OK;
 }

@@ -446,6 +446,9 @@ def main():
     step_gbs = step_bytes / (dev_ms / args.steps * 1e-3) / 1e9
 
     kernel_name, traffic_key, per_pass = scan_kernel_for(b)
+    if traffic_key == "scan_pair64" and st.get("pair_scan_launches", 0) == 0:
+        # the engine fell back to the single-CTA kernel (clusters of two CTAs cannot be resident on this device)
+        kernel_name, traffic_key = "scan_tc_kernel<64> (tcgen05 kind::tf32 3xTF32, 64 queries per pass)", "scan_tc64"
     traffic, traffic_src = load_traffic(traffic_key, n_loc)
     passes_per_step = st["scan_launches"] / args.steps
     # per kernel class (CUDA-event brackets inside the engine): ms per step, share, algorithmic bytes, fraction of peak

@@ -119,6 +119,7 @@ typedef struct ais_stats {
     int64_t kind_launches[AIS_N_KINDS]; /* timed brackets per class */
     int64_t bound_passes;       /* second passes served by the per-tile bound on the blend instead of a streaming pass */
     int64_t bitmap_batches;     /* batches whose BM25 side ran on the term-bitmap path (tf == 1 index) instead of per-tile records */
+    int64_t pair_scan_launches; /* of scan_launches: 64-query passes on CTA pairs (scan_pair_kernel, tcgen05 cta_group::2) */
 } ais_stats;
 
 const char* ais_last_error(void);

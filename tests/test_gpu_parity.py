@@ -182,24 +182,26 @@ def test_tensor_core_scan_accuracy(mb):
     eng.close()
 
 
+@pytest.mark.parametrize("n_batch", [12, 40])
 @pytest.mark.parametrize("n_docs", [11, 33, 127, 129, 300])
-def test_batched_path_on_tiny_indexes(n_docs):
-    """Ragged / single-tile shards through the batched kernels (tcgen05 scan with one partial 128-row tile, BM25 records
-    and tile maxima of a partial 256-doc tile): a 12-query batch returns what twelve single-query searches return."""
+def test_batched_path_on_tiny_indexes(n_docs, n_batch):
+    """Ragged / single-tile shards through the batched kernels (tcgen05 scan with one partial 128-row tile - 40 queries: the
+    CTA-pair kernel, whose second CTA then works on a tile that lies wholly beyond the shard -, BM25 records and tile
+    maxima of a partial 256-doc tile): a batch returns what single-query searches return."""
     from gpu_util import same_ranking
     idx = synth.generate_index(n_docs, vocab_size=40, seed=500 + n_docs)
     t2i = idx.token2id
     infer = lambda words: idx.infer.one([t2i[w] for w in words if w in t2i])
     qs = []
-    for text in synth.generate_queries(idx, 40, seed=n_docs):
+    for text in synth.generate_queries(idx, 40 + 3 * n_batch, seed=n_docs):
         try:
             qs.append(Q.make_query(text, t2i, infer))
         except KeyError:             # the special tag "3:4" parses as tag "3", weight 4 (webui.py:358-371): host-side error
             continue
-    qs = qs[:12]
-    assert len(qs) == 12
+    qs = qs[:n_batch]
+    assert len(qs) == n_batch
     single = E.SearchEngine.from_index(idx, max_batch=1)
-    many = E.SearchEngine.from_index(idx, max_batch=12)
+    many = E.SearchEngine.from_index(idx, max_batch=n_batch)
     for mode in (E.PRF_STORED_ROWS, E.PRF_STORED_ROWS_FULL, E.PRF_OFF):
         ref = [single.search_raw([q], 100, mode) for q in qs]
         got = many.search_raw(qs, 100, mode)
