@@ -59,7 +59,8 @@ typedef struct ais_params {
     double diff_filter_thresh;      /* 1e-6  DIFF_FILTER_THRESH     webui.py:58 */
     double require_magic;           /* 1000  REQUIRE_TAG_MAGIC_NUMBER webui.py:60 */
     int32_t prf_depth;              /* 10    webui.py:193-195 */
-    int32_t max_batch;              /* queries per engine batch (1..256); up to 64 of them share one pass over the doc vectors */
+    int32_t max_batch;              /* queries per engine batch (1..256); up to 64 of them share one pass over the doc vectors
+                                     * (ais_search takes any n_queries and cuts the list into engine batches itself) */
 } ais_params;
 
 /* One weighted tag query, already parsed by the host (webui.py:354-371 stays Python). */
