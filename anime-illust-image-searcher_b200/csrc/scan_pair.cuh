@@ -62,6 +62,30 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// once per kernel (the peer's query images have landed in ITS shared memory, written there by TMA, and the leader's
+// tensor core is about to read them): generic-memory data crosses CTAs here, so this pair is cluster-scoped
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if ((++spins & 0x3FFu) == 0) {
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ll) __trap();
+        }
+    }
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -189,10 +213,11 @@ scan_pair_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_const
         mbar_wait_guarded(b_full, 0, 1);
         if (!leader) {
             // the peer only reports that its query half has landed; the leader issues every MMA of the pair
-            if (lane == 0) mbar_arrive_cluster(mapa_shared(b_peer, 0));
+            fence_proxy_async();                      // TMA (async proxy) wrote the images; the release below publishes them
+            if (lane == 0) mbar_arrive_release_cluster(mapa_shared(b_peer, 0));
             __syncwarp();
         } else {
-            mbar_wait_cluster_guarded(b_peer, 0);
+            mbar_wait_acquire_cluster(b_peer, 0);
             tc_fence_after();
             const uint64_t b_hi0 = tc_desc(base + OFF_BHI), b_lo0 = tc_desc(base + OFF_BLO);
             int it = 0;
