@@ -149,3 +149,51 @@ def test_packed_query_records_match_the_c_struct():
         assert C.addressof(rec[i].term_ids.contents) == q.term_ids.ctypes.data
         assert C.addressof(rec[i].weights.contents) == q.weights.ctypes.data
         assert rec[i].vec[299] == q.vec[299] and rec[i].weights[0] == q.weights[0]
+
+
+def test_merged_prefix_of_short_shard_lists_is_exact():
+    """The argument behind shard.py's short per-shard lists (select.cuh prefix_bound_kernel, mirrored in tests/fake_engine.py):
+    every doc a shard did not return scores at most that shard's last returned key, so the merged list is the true global
+    order strictly above the largest such key (and for its first k entries in any case).  Random scores with ties, random
+    splits: the prefix the rule certifies equals the true global ranking, and it is never shorter than k."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    for case in range(300):
+        n = int(rng.integers(20, 400))
+        shards = int(rng.integers(2, 9))
+        k = int(rng.integers(1, 40))
+        scores = rng.integers(0, 60, size=n).astype(np.float64)         # many ties
+        ids = np.arange(n)
+        cuts = np.sort(rng.choice(np.arange(1, n), size=shards - 1, replace=False))
+        order_all = np.lexsort((ids, -scores))                            # score desc, id asc: the engine's order
+        lists, bound = [], -np.inf
+        for lo, hi in zip(np.r_[0, cuts], np.r_[cuts, n]):
+            o = lo + np.lexsort((ids[lo:hi], -scores[lo:hi]))[:k]
+            lists.append(o)
+            if len(o) == k and hi - lo >= k:                              # a full list: the shard may hold more at <= its last key
+                bound = max(bound, scores[o[-1]])
+        cand = np.concatenate(lists)
+        merged = cand[np.lexsort((ids[cand], -scores[cand]))][:1024]
+        exact = max(min(k, len(merged)), int((scores[merged] > bound).sum()))
+        assert exact >= min(k, len(merged))
+        assert np.array_equal(merged[:exact], order_all[:exact]), (case, n, shards, k)
+
+
+def test_shard_list_depth_policy(monkeypatch):
+    """ShardedSearch asks every shard for kmax / shards + 128 candidates (at least what the result needs, at most half the
+    shard's segment count); AIS_SHARD_CUT=0 restores the single-engine depth."""
+    from types import SimpleNamespace
+    import ais_b200  # noqa: F401
+    from ais_b200 import shard
+    eng = SimpleNamespace(params=SimpleNamespace(prf_depth=10, max_batch=4), max_select_k=lambda: 1024)
+    monkeypatch.delenv("AIS_SELECT_DEPTH", raising=False)
+    monkeypatch.delenv("AIS_SHARD_CUT", raising=False)
+    S = shard.ShardedSearch([eng], 10_000_000)
+    S.n_shards = 8
+    assert S._select_depth(91, 1014) == 256                    # 1024 / 8 + 128
+    assert S._select_depth(500, 1014) == 500                   # never less than the result needs
+    S.n_shards = 1
+    assert S._select_depth(91, 1014) == 977                    # one engine: half of the 1954 segments of 10 M docs
+    S.n_shards = 8
+    monkeypatch.setenv("AIS_SHARD_CUT", "0")
+    assert S._select_depth(91, 1014) == 814                    # 1.25 M docs per shard: 1628 segments / 2
