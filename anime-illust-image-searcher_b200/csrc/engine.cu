@@ -202,7 +202,9 @@ struct ais_engine {
     int col_comp = -1;  const void* col_rows_ptr = nullptr;  int64_t col_n = -1;
     bool rer_column = false;       // current batch: rer[q][d] = colbuf[d] * d_q2[q][col_comp], never materialised
     bool requery_dense = false;    // AIS_REQUERY_DENSE=1: always run the dense scan for the PRF re-query
-    int sel_deep = -1;             // AIS_SELECT_DEPTH: cap on the extra prefix length the select stages ask for (-1: none)
+    int sel_deep = 576;            // AIS_SELECT_DEPTH: cap on the prefix length the select stages ask for beyond need (-1: none).
+                                   // 10 M docs, batch 256, same box: 512 28.64 ms, 640 28.83, 768 29.16, 1024 29.88 per step -
+                                   // deeper lists cost select / pass-2 work, shorter ones bring witness passes back (384: +1.3 ms)
     bool no_bound = true;          // AIS_TILE_BOUND=1: pass 2 of the collapsed re-query skips tiles by an upper bound on R
                                    // (exact, but only selective when BM25 separates the top docs; measured on the benchmark:
                                    // the pass-1-candidate threshold lets > 4096 survivors through for sim-dominated queries)

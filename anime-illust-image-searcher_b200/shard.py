@@ -119,6 +119,8 @@ class ShardedSearch:
         # lists of kmax / n_shards (+ slack for an uneven split) give the same ~kmax-deep exact prefix as one engine
         if self.n_shards > 1 and os.environ.get("AIS_SHARD_CUT", "1") != "0":
             deep = min(deep, -(-self.kmax // self.n_shards) + 128)
+        elif self.n_shards == 1:
+            deep = min(deep, 576)                            # the engine's own default (engine.cu sel_deep)
         env = os.environ.get("AIS_SELECT_DEPTH")
         if env is not None and int(env) >= 0:
             deep = min(deep, int(env))

@@ -193,7 +193,7 @@ def test_shard_list_depth_policy(monkeypatch):
     assert S._select_depth(91, 1014) == 256                    # 1024 / 8 + 128
     assert S._select_depth(500, 1014) == 500                   # never less than the result needs
     S.n_shards = 1
-    assert S._select_depth(91, 1014) == 977                    # one engine: half of the 1954 segments of 10 M docs
+    assert S._select_depth(91, 1014) == 576                    # one engine: the engine's own default cap (engine.cu sel_deep)
     S.n_shards = 8
     monkeypatch.setenv("AIS_SHARD_CUT", "0")
     assert S._select_depth(91, 1014) == 814                    # 1.25 M docs per shard: 1628 segments / 2
