@@ -514,7 +514,7 @@ def main():
         S.trace = False
         stage_ms = {k: v / max(1, S.traced_steps) for k, v in S.stage_ms.items()}
     fixed = None
-    if not args.no_modes:
+    if not args.no_modes and world == 1:             # N > 1: stage_ms_per_step above shows the same thing per stage
         try:
             n_small = 8192 * world
             e0 = stage(n_small, min(256, b))[0]
